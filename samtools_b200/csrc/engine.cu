@@ -1,0 +1,773 @@
+// engine.cu -- B200 (sm_100a) pileup engine: device buffers, the read stage,
+// the column stage and the C ABI declared in include/b200_pileup.h.
+//
+// Data layout in HBM (one staged batch = the reads of one reference sequence
+// overlapping one window, grouped by input file, file order kept):
+//   raw SoA     pos i64 | flag u16 | mapq u8 | l_qseq i32 | n_cigar u32 |
+//               cigar_off u64 | qual_off u64 | mtid i32 | mpos i64 | isize i64 |
+//               prev_same_name i64 | rbits u8          (one array per field)
+//   payload     cigar u32[] | seq4 u8[] (4-bit) | qual u8[] | ref char[]
+//   derived     ReadDesc[32 B] per read, prefix-max of read ends, per-32-column
+//               [lo,hi) read ranges, look-back status words, output text
+//
+// Column stage = one thread per reference position.  A CTA owns 128 adjacent
+// columns: (1) every thread sizes its output line by walking the reads whose
+// range covers its warp's 32 columns, (2) a block scan + decoupled look-back
+// across CTAs (ticket-ordered, single pass) gives the CTA its byte offset in
+// the output, (3) the lines are formatted into shared memory laid out with the
+// same 16-byte phase as the destination and (4) leave the SM as one
+// cp.async.bulk (TMA) shared->global store plus <16 B ragged edges.
+// HBM traffic per column is therefore ~ the algorithmic bytes: reads are
+// fetched once through L1/L2 (neighbouring columns share them), text is
+// written once, fully coalesced.  No tensor cores: integer/byte work.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <queue>
+
+#include "../../include/b200_pileup.h"
+#include "plp_core.h"
+#include "plp_stage.h"
+#include "engine_internal.h"
+
+using namespace plp;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    snprintf(e->err, sizeof e->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return -1; } } while (0)
+
+// ============================== device helpers ===============================
+__device__ __forceinline__ uint64_t ld_acquire_u64(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+#define ST_FLAG(w) ((w) >> 62)
+#define ST_VAL(w) ((w) & 0x3fffffffffffffffULL)
+
+// decoupled look-back (sum): returns the exclusive prefix of tile `t`
+__device__ uint64_t lookback_sum(uint64_t *st, int t, uint64_t agg)
+{
+    if (t == 0) { st_release_u64(&st[0], (2ULL << 62) | agg); return 0; }
+    st_release_u64(&st[t], (1ULL << 62) | agg);
+    uint64_t excl = 0;
+    for (int j = t - 1;; --j) {
+        uint64_t w;
+        while (ST_FLAG(w = ld_acquire_u64(&st[j])) == 0) { __nanosleep(20); }
+        excl += ST_VAL(w);
+        if (ST_FLAG(w) == 2) break;
+    }
+    st_release_u64(&st[t], (2ULL << 62) | (excl + agg));
+    return excl;
+}
+
+template <int T>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_sums, uint32_t &total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane < T / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        if (lane < T / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    total = warp_sums[T / 32 - 1];
+    uint32_t base = w ? warp_sums[w - 1] : 0;
+    return base + x - v;
+}
+
+// ============================== read stage ===================================
+// (arithmetic in plp_stage.h; one thread per read)
+__global__ void k_prep1(RawSoA r, b200_stage_conf_t cf, uint8_t *state, int32_t *rlen_out, StageAcc *acc)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r.n) stage_prep1(r, cf, i, state, rlen_out, acc);
+}
+__global__ void k_prep2(RawSoA r, b200_stage_conf_t cf, uint8_t *state)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r.n) stage_prep2(r, cf, i, state);
+}
+__global__ void k_build_desc(RawSoA r, b200_stage_conf_t cf, const uint8_t *state, const int32_t *rlen,
+                             ReadDesc *desc, int32_t *endv, StageAcc *acc, int64_t win_base, int32_t *cig_x, int32_t *cig_y)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r.n) stage_build_desc(r, cf, i, state, rlen, desc, endv, acc, win_base, cig_x, cig_y);
+}
+
+// inclusive prefix max of endv[] (single pass, decoupled look-back, one file at a time)
+__global__ void k_scan_max(const int32_t *in, int32_t *out, int64_t n, uint64_t *st, uint32_t *ticket)
+{
+    constexpr int T = 256, IPT = 8;
+    __shared__ int s_tile;
+    __shared__ int32_t s_w[T / 32];
+    __shared__ int32_t s_excl;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int t = s_tile;
+    const int64_t base = (int64_t)t * T * IPT + (int64_t)threadIdx.x * IPT;
+    int32_t v[IPT], m = INT32_MIN;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) { v[j] = base + j < n ? in[base + j] : INT32_MIN; m = max(m, v[j]); v[j] = m; }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int32_t x = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x = max(x, y); }
+    if (lane == 31) s_w[w] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t run = INT32_MIN;
+        for (int k = 0; k < T / 32; ++k) { int32_t tmp = s_w[k]; s_w[k] = run; run = max(run, tmp); }
+        // publish aggregate / look back (values biased to unsigned)
+        const uint64_t agg = (uint64_t)((int64_t)run - INT32_MIN);
+        uint64_t excl = 0;
+        if (t == 0) st_release_u64(&st[0], (2ULL << 62) | agg);
+        else {
+            st_release_u64(&st[t], (1ULL << 62) | agg);
+            for (int j = t - 1;; --j) {
+                uint64_t wv;
+                while (ST_FLAG(wv = ld_acquire_u64(&st[j])) == 0) { __nanosleep(20); }
+                { const uint64_t pv = ST_VAL(wv); if (pv > excl) excl = pv; }
+                if (ST_FLAG(wv) == 2) break;
+            }
+            st_release_u64(&st[t], (2ULL << 62) | (excl > agg ? excl : agg));
+        }
+        s_excl = (int32_t)((int64_t)excl + INT32_MIN);
+    }
+    __syncthreads();
+    int32_t pre = max(s_excl, s_w[w]);
+    int32_t left = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane > 0) pre = max(pre, left);
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) if (base + j < n) out[base + j] = max(pre, v[j]);
+}
+
+// per 32-column group: the [lo,hi) slice of each file's reads that can cover it
+__global__ void k_ranges(const ReadDesc *desc, const int32_t *pmax, const int64_t *file_start, int n_files,
+                         int32_t n_groups, int32_t *glo, int32_t *ghi, int *max_range)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_groups * n_files) return;
+    const int f = (int)(idx / n_groups), g = (int)(idx % n_groups);
+    const int64_t fs = file_start[f], fe = file_start[f + 1];
+    const int32_t c0 = g * 32, c1 = c0 + 31;
+    int64_t lo = fs, hi = fe;
+    while (lo < hi) { int64_t m = (lo + hi) >> 1; if (pmax[m] > c0) hi = m; else lo = m + 1; }   // first read whose running max end exceeds c0
+    const int64_t first = lo;
+    lo = first; hi = fe;
+    while (lo < hi) { int64_t m = (lo + hi) >> 1; if (desc[m].rpos > c1) hi = m; else lo = m + 1; }  // first read starting beyond c1
+    glo[idx] = (int32_t)first;
+    const int64_t last = lo > first ? lo : first;
+    ghi[idx] = (int32_t)last;
+    atomicMax(max_range, (int)(last - first));
+}
+
+// ============================== column stage =================================
+constexpr int TILE = 128;
+
+// shared->global bulk store (TMA engine, SASS UBLKCP); all addresses/sizes 16 B aligned
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Shared skeleton of the text-producing kernels.  Fmt provides
+//   uint32_t size(int32_t c, State&)   and   void write(int32_t c, const State&, char*)
+template <class Fmt>
+__device__ __forceinline__ void text_tile(const Fmt &fmt, int32_t ncols, char *out, uint64_t *status, uint32_t *ticket,
+                                          unsigned long long *total_out, uint32_t smem_cap, int use_tma)
+{
+    extern __shared__ __align__(16) char s_text[];
+    __shared__ uint32_t s_ws[TILE / 32];
+    __shared__ int s_tile;
+    __shared__ uint64_t s_base;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int t = s_tile;
+    const int32_t c = t * TILE + (int32_t)threadIdx.x;
+    typename Fmt::State stt;
+    uint32_t len = c < ncols ? fmt.size(c, stt) : 0;
+    uint32_t total;
+    const uint32_t off = block_excl_scan<TILE>(len, s_ws, total);
+    if (threadIdx.x == 0) {
+        s_base = lookback_sum(status, t, total);
+        if (t == (int)gridDim.x - 1) *total_out = s_base + total;
+    }
+    __syncthreads();
+    const uint64_t base = s_base;
+    if (total == 0) return;
+    const uint32_t phase = (uint32_t)(base & 15);
+    if (total + phase <= smem_cap) {
+        char *sb = s_text + phase;
+        if (len) fmt.write(c, stt, sb + off);
+        __syncthreads();
+        // ragged head (to the next 16 B boundary of the destination), aligned body, ragged tail
+        char *g = out + base;
+        const uint32_t head = min(total, (16u - phase) & 15u);
+        const uint32_t body = (total - head) & ~15u;
+        const uint32_t tail = total - head - body;
+        if (threadIdx.x < head) g[threadIdx.x] = sb[threadIdx.x];
+        if (threadIdx.x < tail) g[head + body + threadIdx.x] = sb[head + body + threadIdx.x];
+        if (body) {
+            if (use_tma) {
+                if (threadIdx.x == 0) bulk_store_s2g(g + head, sb + head, body);
+            } else {
+                const uint4 *src = reinterpret_cast<const uint4 *>(sb + head);
+                uint4 *dst = reinterpret_cast<uint4 *>(g + head);
+                for (uint32_t i = threadIdx.x; i < body / 16; i += TILE) dst[i] = src[i];
+            }
+        }
+    } else if (len) {
+        fmt.write(c, stt, out + base + off);   // very deep tile: format straight into HBM
+    }
+}
+
+struct MpFmt {
+    View v; MpConf cf;
+    typedef MpFileSz State;
+    __device__ __forceinline__ uint32_t size(int32_t c, State &s) const { return mp_line_size(v, cf, c >> 5, c, s); }
+    __device__ __forceinline__ void write(int32_t c, const State &s, char *p) const { mp_line_write(v, cf, c >> 5, c, s, p); }
+};
+
+__global__ void __launch_bounds__(TILE) k_mpileup(MpFmt fmt, char *out, uint64_t *status, uint32_t *ticket,
+                                                  unsigned long long *total_out, uint32_t smem_cap, int use_tma)
+{
+    text_tile(fmt, fmt.v.ncols, out, status, ticket, total_out, smem_cap, use_tma);
+}
+
+// depth rows "name\tpos(\tdepth)*\n" (bam2depth.c:234-244)
+struct DpFmt {
+    View v; DpConf cf;
+    struct State { int32_t d0; };
+    __device__ __forceinline__ uint32_t size(int32_t c, State &s) const
+    {
+        bool any = false; uint32_t body = 0;
+        for (int f = 0; f < v.n_files; ++f) {
+            DpCol o; dp_file_column(v, cf, f, c >> 5, c, o);
+            if (f == 0) s.d0 = o.depth;
+            any |= o.spanned;
+            body += 1 + (uint32_t)ndigits((uint64_t)o.depth);
+        }
+        if (!any && !(cf.all && c < v.ncols_all)) return 0;
+        if (!bed_pass(v, c)) return 0;
+        return (uint32_t)v.name_len + 1 + (uint32_t)ndigits((uint64_t)(v.win_base + c + 1)) + body + 1;
+    }
+    __device__ __forceinline__ void write(int32_t c, const State &s, char *p) const
+    {
+        for (int i = 0; i < v.name_len; ++i) *p++ = v.name[i];
+        *p++ = '\t';
+        p += put_u64(p, (uint64_t)(v.win_base + c + 1));
+        for (int f = 0; f < v.n_files; ++f) {
+            int32_t d = s.d0;
+            if (f) { DpCol o; dp_file_column(v, cf, f, c >> 5, c, o); d = o.depth; }
+            *p++ = '\t';
+            p += put_u64(p, (uint64_t)d);
+        }
+        *p = '\n';
+    }
+};
+
+__global__ void __launch_bounds__(TILE) k_depth(DpFmt fmt, char *out, uint64_t *status, uint32_t *ticket,
+                                                unsigned long long *total_out, uint32_t smem_cap, int use_tma)
+{
+    text_tile(fmt, fmt.v.ncols, out, status, ticket, total_out, smem_cap, use_tma);
+}
+
+// coverage column sums (coverage.c:622-660)
+__global__ void __launch_bounds__(256) k_coverage(View v, int32_t min_baseQ, int32_t min_depth, unsigned long long *sums)
+{
+    const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    unsigned long long a[5] = {0, 0, 0, 0, 0};
+    if (c < v.ncols) {
+        CvCol o; cv_column(v, min_baseQ, c >> 5, c, o);
+        a[4] = o.missing;
+        if (o.count_base && o.depth >= (uint32_t)min_depth) { a[0] = 1; a[1] = o.depth; a[2] = o.sum_bq; a[3] = o.qbases; }
+    }
+    __shared__ unsigned long long s[5][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        unsigned long long x = a[k];
+        for (int o = 16; o; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) s[k][w] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        unsigned long long x = 0;
+        for (int k = 0; k < 8; ++k) x += s[threadIdx.x][k];
+        if (x) atomicAdd(&sums[threadIdx.x], x);
+    }
+}
+
+// column-major pileup entries for the iterator tier: counts, then entries
+__global__ void k_entries_count(View v, int f, uint32_t *col_n)
+{
+    const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= v.ncols) return;
+    const int g = c >> 5;
+    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + g], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + g];
+    uint32_t n = 0;
+    for (int32_t i = lo_; i < hi_; ++i) { const ReadDesc d = v.desc[i]; if (c >= d.rpos && c < d.rend) ++n; }
+    col_n[c] = n;
+}
+__global__ void k_entries_fill(View v, int f, const uint64_t *col_off, b200_pileup1_t *ents, int64_t file_first)
+{
+    const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= v.ncols) return;
+    const int g = c >> 5;
+    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + g], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + g];
+    b200_pileup1_t *o = ents + col_off[c];
+    for (int32_t i = lo_; i < hi_; ++i) {
+        const ReadDesc d = v.desc[i];
+        if (c < d.rpos || c >= d.rend) continue;
+        Ent e; resolve(v, d, c, e);
+        if (e.k < 0) {   // simple read: the op index of its match
+            const uint32_t *cg = v.cigar + d.cig_off; int k = 0;
+            while (!is_mop(cg[k] & 0xf)) ++k;
+            e.k = k;
+        }
+        b200_pileup1_t p;
+        p.read = i; p.qpos = e.qpos; p.indel = e.indel; p.cigar_ind = e.k;
+        p.is_del = e.is_del; p.is_head = e.is_head; p.is_tail = e.is_tail; p.is_refskip = e.is_refskip;
+        *o++ = p;
+    }
+    (void)file_first;
+}
+__global__ void k_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int32_t n, uint64_t *st, uint32_t *ticket)
+{
+    constexpr int T = 256;
+    __shared__ uint32_t s_ws[T / 32];
+    __shared__ int s_tile; __shared__ uint64_t s_base;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int t = s_tile;
+    const int32_t i = t * T + (int32_t)threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0, total;
+    uint32_t off = block_excl_scan<T>(v, s_ws, total);
+    if (threadIdx.x == 0) s_base = lookback_sum(st, t, total);
+    __syncthreads();
+    if (i < n) out[i] = s_base + off;
+    if (i == n - 1) out[n] = s_base + off + v;
+}
+
+// ============================== host side ====================================
+template <class T> static int ensure(b200_engine *e, T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap && p) return 0;
+    if (p) cudaFree(p);
+    size_t nc = need + need / 8 + 256;
+    p = nullptr; cap = 0;
+    CK(cudaMalloc((void **)&p, nc * sizeof(T)));
+    cap = nc;
+    return 0;
+}
+#define ENSURE(field, need) do { if (ensure(e, e->field, e->cap_##field, (need))) return -1; } while (0)
+
+static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+#include "overlap.cuh"
+#include "baq.cuh"
+
+extern "C" const char *b200_version(void) { return "samtools_b200 0.1 (sm_100a)"; }
+extern "C" const char *b200_last_error(const b200_engine_t *e) { return e ? e->err : "null engine"; }
+extern "C" double b200_last_kernel_ms(const b200_engine_t *e) { return e->last_kernel_ms; }
+extern "C" double b200_last_stage_ms(const b200_engine_t *e) { return e->last_stage_ms; }
+extern "C" int64_t b200_launch_count(const b200_engine_t *e) { return e->launches; }
+
+extern "C" int b200_engine_create(int device, b200_engine_t **out)
+{
+    *out = nullptr;
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n <= 0) {
+        fprintf(stderr, "[b200_pileup] no CUDA device: %s (this engine has no CPU fallback)\n", cudaGetErrorString(ce));
+        return -1;
+    }
+    if (device < 0 || device >= n) { fprintf(stderr, "[b200_pileup] bad device %d of %d\n", device, n); return -1; }
+    b200_engine *e = new b200_engine();
+    e->device = device;
+    e->err[0] = 0;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fprintf(stderr, "[b200_pileup] cannot initialise device %d\n", device);
+        delete e;
+        return -1;
+    }
+    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
+    e->smem_text = 40 * 1024;
+    const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
+    s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
+    cudaFuncSetAttribute(k_mpileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
+    cudaFuncSetAttribute(k_depth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
+    cudaMalloc((void **)&e->d_acc, sizeof(StageAcc));
+    cudaMalloc((void **)&e->d_misc, 64 * sizeof(unsigned long long));
+    *out = e;
+    return 0;
+}
+
+extern "C" void b200_engine_destroy(b200_engine_t *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    e->free_all();
+    cudaFree(e->d_acc); cudaFree(e->d_misc);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+template <class T> static int h2d(b200_engine *e, T *&dp, size_t &cap, const T *hp, size_t n)
+{
+    if (ensure(e, dp, cap, n ? n : 1)) return -1;
+    if (n && hp) CK(cudaMemcpyAsync(dp, hp, n * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+    return 0;
+}
+#define H2D(field, hp, n) do { if (h2d(e, e->field, e->cap_##field, (hp), (size_t)(n))) return -1; } while (0)
+
+
+// max-depth rule of bam_plp_push, evaluated on the host only when a column could
+// hold more than maxcnt reads (sequential by nature).
+static int apply_maxcnt_host(b200_engine *e, int64_t n, int maxcnt)
+{
+    std::vector<ReadDesc> hd((size_t)n);
+    std::vector<uint8_t> st((size_t)n);
+    CK(cudaMemcpyAsync(hd.data(), e->desc, (size_t)n * sizeof(ReadDesc), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(st.data(), e->state, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    bool changed = false;
+    for (int f = 0; f < e->n_files; ++f) {
+        std::priority_queue<int32_t, std::vector<int32_t>, std::greater<int32_t>> ends;  // accepted reads still buffered
+        bool have_prev = false; int32_t p_prev = 0;
+        for (int64_t i = e->h_file_start[f]; i < e->h_file_start[f + 1]; ++i) {
+            if (st[i] != ST_KEEP) continue;
+            const int32_t pos = hd[i].rpos, end = hd[i].rpos + e->h_rlen_tmp[i];
+            if (have_prev) {
+                while (!ends.empty() && ends.top() < p_prev) ends.pop();   // buffered = accepted reads with end >= previous accepted start
+                if (pos == p_prev && (int64_t)ends.size() + 1 > (int64_t)maxcnt) { st[i] = ST_MAXDROP; changed = true; continue; }
+            }
+            ends.push(end);
+            have_prev = true; p_prev = pos;
+        }
+    }
+    if (changed) CK(cudaMemcpyAsync(e->state, st.data(), (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    e->maxdrop_applied = changed;
+    return 0;
+}
+
+__global__ void k_apply_maxdrop(const uint8_t *state, ReadDesc *desc, int32_t *endv, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (state[i] == ST_MAXDROP) { desc[i].rend = desc[i].rpos; endv[i] = INT32_MIN; }
+}
+
+extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t *cf, b200_stage_stats_t *stats)
+{
+    if (!e || !b || !cf) return -1;
+    CK(cudaSetDevice(e->device));
+    const int64_t n = b->n_reads;
+    if (b->n_files < 1) { snprintf(e->err, sizeof e->err, "n_files < 1"); return -1; }
+    if (n >= (1LL << 31)) { snprintf(e->err, sizeof e->err, "batch too large (%lld reads)", (long long)n); return -1; }
+    for (int64_t i = 0; i < 0; ++i) {}
+    CK(cudaEventRecord(e->ev0, e->stream));
+    e->n = n; e->n_files = b->n_files; e->tid = b->tid; e->tid_len = b->tid_len;
+    e->name = b->tid_name ? b->tid_name : "";
+    e->sconf = *cf;
+    e->win_base = cf->beg > 0 ? cf->beg : 0;
+    e->h_file_start.assign(b->file_start, b->file_start + b->n_files + 1);
+    // ---- H2D
+    H2D(pos, b->pos, n); H2D(flag, b->flag, n); H2D(mapq, b->mapq, n); H2D(l_qseq, b->l_qseq, n);
+    H2D(n_cigar, b->n_cigar, n); H2D(cigar_off, b->cigar_off, n); H2D(qual_off, b->qual_off, n);
+    H2D(mtid, b->mtid, n); H2D(mpos, b->mpos, n); H2D(isize, b->isize, n);
+    e->has_prev = b->prev_same_name != nullptr;
+    if (e->has_prev) H2D(prev, b->prev_same_name, n);
+    e->has_rbits = b->rbits != nullptr;
+    if (e->has_rbits) H2D(rbits, b->rbits, n);
+    H2D(cigar, b->cigar, b->n_cigar_total);
+    H2D(seq4, b->seq4, (b->qual_bytes + 1) / 2 + 1);
+    H2D(qual, b->qual, b->qual_bytes + 1);
+    H2D(file_start, b->file_start, b->n_files + 1);
+    e->has_ref = b->ref != nullptr && b->ref_len > 0;
+    if (e->has_ref) H2D(ref, b->ref, b->ref_n);
+    e->ref_beg = b->ref_beg; e->ref_n = b->ref_n; e->ref_len = e->has_ref ? b->ref_len : 0;
+    {
+        size_t nl = strlen(e->name.c_str());
+        H2D(dname, e->name.c_str(), nl + 1);
+    }
+    ENSURE(state, (size_t)n + 1); ENSURE(rlen, (size_t)n + 1); ENSURE(desc, (size_t)n + 1);
+    ENSURE(endv, (size_t)n + 1); ENSURE(pmax, (size_t)n + 1);
+    ENSURE(cig_x, (size_t)b->n_cigar_total + 1); ENSURE(cig_y, (size_t)b->n_cigar_total + 1);
+    CK(cudaMemsetAsync(e->d_acc, 0, sizeof(StageAcc), e->stream));
+    {
+        StageAcc z; memset(&z, 0, sizeof z); z.max_rend = INT32_MIN;
+        CK(cudaMemcpyAsync(e->d_acc, &z, sizeof z, cudaMemcpyHostToDevice, e->stream));
+    }
+    RawSoA r;
+    r.pos = e->pos; r.flag = e->flag; r.mapq = e->mapq; r.l_qseq = e->l_qseq; r.n_cigar = e->n_cigar;
+    r.cigar_off = e->cigar_off; r.qual_off = e->qual_off; r.mtid = e->mtid; r.mpos = e->mpos; r.isize = e->isize;
+    r.prev = e->has_prev ? e->prev : nullptr; r.rbits = e->has_rbits ? e->rbits : nullptr;
+    r.cigar = e->cigar; r.seq4 = e->seq4; r.qual = e->qual;
+    r.ref = e->has_ref ? e->ref : nullptr; r.ref_beg = e->ref_beg; r.ref_n = e->ref_n; r.ref_len = e->ref_len;
+    r.n = n; r.tid = b->tid;
+    StageAcc *acc = (StageAcc *)e->d_acc;
+    if (n > 0) {
+        k_prep1<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, acc); e->launches++;
+        if (cf->mode == B200_MODE_MPILEUP && cf->baq && e->has_ref) { if (launch_baq(e, r, *cf)) return -1; }
+        k_prep2<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state); e->launches++;
+        k_build_desc<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, e->desc, e->endv, acc, e->win_base, e->cig_x, e->cig_y); e->launches++;
+    }
+    CK(cudaGetLastError());
+    // ---- statistics back (also the sync point that validates the batch)
+    StageAcc ha;
+    CK(cudaMemcpyAsync(&ha, e->d_acc, sizeof ha, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->acc_n_kept = (int64_t)ha.n_kept; e->max_rend = ha.n_kept ? ha.max_rend : 0;
+    e->sum_rlen = ha.sum_rlen; e->sum_indel_text = ha.sum_indel_text;
+    // ---- column domain
+    {
+        int64_t wend = cf->end - e->win_base;                       // exclusive, relative
+        int64_t cov = e->max_rend > 0 ? e->max_rend : 0;
+        if (cov > wend) cov = wend;
+        int64_t allc = (cf->end < b->tid_len ? cf->end : b->tid_len) - e->win_base;
+        if (allc < 0) allc = 0;
+        e->ncols_cov = cov; e->ncols_all = allc;
+        int64_t nc = cov > allc ? cov : allc;
+        if (nc >= (1LL << 31) - 4096) { snprintf(e->err, sizeof e->err, "window too wide (%lld columns)", (long long)nc); return -1; }
+        e->ncols_max = (int32_t)nc;
+    }
+    e->n_groups = (e->ncols_max + 31) / 32 + 1;
+    ENSURE(glo, (size_t)e->n_groups * e->n_files + 1); ENSURE(ghi, (size_t)e->n_groups * e->n_files + 1);
+    e->maxdrop_applied = false;
+    int max_range = 0;
+    if (n > 0) {
+        if (build_ranges(e, &max_range)) return -1;
+        // max-depth rule (bam_plp_push): only reachable when some column can hold > maxcnt reads
+        if (cf->mode != B200_MODE_DEPTH && cf->max_depth > 0 && 2LL * max_range + 1 > (int64_t)cf->max_depth) {
+            e->h_rlen_tmp.resize((size_t)n);
+            CK(cudaMemcpyAsync(e->h_rlen_tmp.data(), e->rlen, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+            if (apply_maxcnt_host(e, n, cf->max_depth)) return -1;
+            if (e->maxdrop_applied) {
+                k_apply_maxdrop<<<nblk(n, 256), 256, 0, e->stream>>>(e->state, e->desc, e->endv, n); e->launches++;
+                if (build_ranges(e, &max_range)) return -1;
+            }
+        }
+        if (cf->mode == B200_MODE_MPILEUP && cf->overlaps && e->has_prev) { if (launch_overlap(e, r)) return -1; }
+        if (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps && e->has_prev) { if (launch_depth_clip(e, r)) return -1; }
+        else e->has_clip = false;
+    } else {
+        CK(cudaMemsetAsync(e->glo, 0, ((size_t)e->n_groups * e->n_files) * 4, e->stream));
+        CK(cudaMemsetAsync(e->ghi, 0, ((size_t)e->n_groups * e->n_files) * 4, e->stream));
+        e->has_clip = false;
+    }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_stage_ms = ms;
+    e->staged = true;
+    if (stats) {
+        stats->n_kept = (int64_t)ha.n_kept; stats->n_kept_in_window = (int64_t)ha.n_kept_in_window;
+        stats->n_reads = ha.n_reads; stats->n_selected_reads = ha.n_selected; stats->summed_mapq = ha.summed_mapq;
+        stats->out_bound = e->text_bound(27, 1);
+        stats->n_cols = e->ncols_max;
+    }
+    return 0;
+}
+
+int build_ranges(b200_engine *e, int *max_range)
+{
+    const int64_t n = e->n;
+    // prefix max of read ends, file by file
+    for (int f = 0; f < e->n_files; ++f) {
+        const int64_t fs = e->h_file_start[f], fn = e->h_file_start[f + 1] - fs;
+        if (fn <= 0) continue;
+        const int nb = nblk(fn, 256 * 8);
+        ENSURE(status, (size_t)nb + 1);
+        CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
+        CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
+        k_scan_max<<<nb, 256, 0, e->stream>>>(e->endv + fs, e->pmax + fs, fn, e->status, (uint32_t *)e->d_misc); e->launches++;
+    }
+    CK(cudaMemsetAsync(e->d_misc + 1, 0, 8, e->stream));
+    const int64_t tot = (int64_t)e->n_groups * e->n_files;
+    k_ranges<<<nblk(tot, 256), 256, 0, e->stream>>>(e->desc, e->pmax, e->file_start, e->n_files, e->n_groups, e->glo, e->ghi, (int *)(e->d_misc + 1));
+    e->launches++;
+    CK(cudaMemcpyAsync(max_range, e->d_misc + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    (void)n;
+    return 0;
+}
+
+static void fill_view(b200_engine *e, View &v, const int64_t *bed_beg, const int64_t *bed_end, int n_bed, int bed_active, int all)
+{
+    v.desc = e->desc; v.cigar = e->cigar; v.cig_x = e->cig_x; v.cig_y = e->cig_y; v.seq4 = e->seq4; v.qual = e->qual;
+    v.clip = e->has_clip ? e->clip : nullptr;
+    v.ref = e->has_ref ? e->ref : nullptr;
+    v.ref_off = e->ref_beg - e->win_base; v.ref_n = e->ref_n; v.ref_len_rel = e->ref_len - e->win_base;
+    v.n_files = e->n_files; v.file_start = e->file_start;
+    v.tile_lo = e->glo; v.tile_hi = e->ghi; v.n_tiles = e->n_groups; v.tile_cols = 32;
+    v.win_base = e->win_base;
+    v.ncols_all = all ? (int32_t)e->ncols_all : 0;
+    v.ncols = (int32_t)(all ? std::max(e->ncols_cov, e->ncols_all) : e->ncols_cov);
+    v.name = e->dname; v.name_len = (int32_t)e->name.size();
+    v.bed_beg = bed_beg; v.bed_end = bed_end; v.n_bed = n_bed; v.bed_active = bed_active;
+}
+
+static int upload_bed(b200_engine *e, const int64_t *bb, const int64_t *be, int n, int active)
+{
+    if (!active) return 0;
+    H2D(bed_beg, bb, n); H2D(bed_end, be, n);
+    return 0;
+}
+
+template <class Fmt, class K>
+static int run_text(b200_engine *e, K kernel, const Fmt &fmt, uint64_t bound, char *out, size_t out_cap, size_t *out_len)
+{
+    const int32_t ncols = fmt.v.ncols;
+    const int nt = (ncols + TILE - 1) / TILE;
+    *out_len = 0;
+    e->last_kernel_ms = 0;
+    if (nt == 0) return 0;
+    ENSURE(out, (size_t)bound + 64);
+    ENSURE(status, (size_t)nt + 1);
+    CK(cudaMemsetAsync(e->status, 0, ((size_t)nt + 1) * 8, e->stream));
+    CK(cudaMemsetAsync(e->d_misc, 0, 16, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    kernel<<<nt, TILE, e->smem_text + 16, e->stream>>>(fmt, e->out, e->status, (uint32_t *)e->d_misc, e->d_misc + 1, e->smem_text, e->use_tma);
+    e->launches++;
+    CK(cudaEventRecord(e->ev1, e->stream));
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, e->d_misc + 1, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
+    if (total > bound) { snprintf(e->err, sizeof e->err, "internal: output %llu exceeds bound %llu", total, (unsigned long long)bound); return -1; }
+    *out_len = (size_t)total;
+    e->last_out_len = (size_t)total;
+    if (out) {
+        if (total > out_cap) { snprintf(e->err, sizeof e->err, "output buffer too small: need %llu bytes", total); return -2; }
+        CK(cudaMemcpyAsync(out, e->out, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
+}
+
+extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out, size_t out_cap, size_t *out_len)
+{
+    if (!e || !e->staged) { if (e) snprintf(e->err, sizeof e->err, "no staged batch"); return -1; }
+    CK(cudaSetDevice(e->device));
+    if (upload_bed(e, c->bed_beg, c->bed_end, c->n_bed, c->bed_active)) return -1;
+    MpFmt fmt;
+    fill_view(e, fmt.v, e->bed_beg, e->bed_end, c->n_bed, c->bed_active, c->all);
+    fmt.cf.min_baseQ = c->min_baseQ; fmt.cf.all = c->all; fmt.cf.rev_del = c->rev_del; fmt.cf.no_ins = c->no_ins;
+    fmt.cf.no_del = c->no_del; fmt.cf.no_ends = c->no_ends; fmt.cf.out_mapq = c->out_mapq; fmt.cf.out_qpos = c->out_qpos;
+    fmt.cf.out_qpos5 = c->out_qpos5; fmt.cf.n_star_cols = c->n_star_cols;
+    const int per = 2 + (c->out_mapq ? 1 : 0) + (c->out_qpos ? 12 : 0) + (c->out_qpos5 ? 13 : 0);
+    const uint64_t bound = e->text_bound(per, 1 + 2 * (3 + c->n_star_cols)) ;
+    return run_text(e, k_mpileup, fmt, bound, out, out_cap, out_len);
+}
+
+extern "C" int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, char *out, size_t out_cap, size_t *out_len)
+{
+    if (!e || !e->staged) { if (e) snprintf(e->err, sizeof e->err, "no staged batch"); return -1; }
+    CK(cudaSetDevice(e->device));
+    if (upload_bed(e, c->bed_beg, c->bed_end, c->n_bed, c->bed_active)) return -1;
+    DpFmt fmt;
+    fill_view(e, fmt.v, e->bed_beg, e->bed_end, c->n_bed, c->bed_active, c->all);
+    fmt.cf.min_qual = c->min_qual; fmt.cf.count_del = c->count_del; fmt.cf.all = c->all;
+    const uint64_t ncols = (uint64_t)fmt.v.ncols;
+    const uint64_t bound = ncols * (e->name.size() + 1 + 20 + (uint64_t)e->n_files * 12 + 1) + 64;
+    return run_text(e, k_depth, fmt, bound, out, out_cap, out_len);
+}
+
+extern "C" int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b200_coverage_sums_t *sums)
+{
+    if (!e || !e->staged) { if (e) snprintf(e->err, sizeof e->err, "no staged batch"); return -1; }
+    CK(cudaSetDevice(e->device));
+    View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);
+    memset(sums, 0, sizeof *sums);
+    CK(cudaMemsetAsync(e->d_misc + 8, 0, 5 * 8, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    if (v.ncols > 0) { k_coverage<<<nblk(v.ncols, 256), 256, 0, e->stream>>>(v, c->min_baseQ, c->min_depth, e->d_misc + 8); e->launches++; }
+    CK(cudaEventRecord(e->ev1, e->stream));
+    unsigned long long h[5];
+    CK(cudaMemcpyAsync(h, e->d_misc + 8, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
+    sums->n_covered_bases = h[0]; sums->summed_coverage = h[1]; sums->summed_baseQ = h[2]; sums->quality_bases = h[3]; sums->missing_qual = h[4];
+    return 0;
+}
+
+extern "C" int b200_fetch_qual(b200_engine_t *e, uint8_t *qual, size_t cap)
+{
+    if (!e || !e->staged) return -1;
+    CK(cudaSetDevice(e->device));
+    size_t nbytes = std::min(cap, e->cap_qual);
+    CK(cudaMemcpy(qual, e->qual, nbytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int b200_fetch_mapq_keep(b200_engine_t *e, uint8_t *mapq, uint8_t *keep, size_t n)
+{
+    if (!e || !e->staged) return -1;
+    CK(cudaSetDevice(e->device));
+    n = std::min(n, (size_t)e->n);
+    if (mapq) CK(cudaMemcpy(mapq, e->mapq, n, cudaMemcpyDeviceToHost));
+    if (keep) CK(cudaMemcpy(keep, e->state, n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int b200_pileup_entries(b200_engine_t *e, int32_t file, int64_t beg, int64_t end, uint32_t *col_n,
+                                   b200_pileup1_t *entries, size_t cap_entries, size_t *n_entries)
+{
+    if (!e || !e->staged) { if (e) snprintf(e->err, sizeof e->err, "no staged batch"); return -1; }
+    CK(cudaSetDevice(e->device));
+    if (file < 0 || file >= e->n_files) { snprintf(e->err, sizeof e->err, "bad file index"); return -1; }
+    View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);
+    int64_t rb = beg - e->win_base, re = end - e->win_base;
+    if (rb < 0) rb = 0;
+    if (re > v.ncols) re = v.ncols;
+    *n_entries = 0;
+    if (re <= rb) return 0;
+    v.ncols = (int32_t)re;
+    ENSURE(col_n, (size_t)re + 1); ENSURE(col_off, (size_t)re + 2);
+    k_entries_count<<<nblk(re, 256), 256, 0, e->stream>>>(v, file, e->col_n); e->launches++;
+    const int nb = nblk(re, 256);
+    ENSURE(status, (size_t)nb + 1);
+    CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
+    CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
+    k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->col_n, e->col_off, (int32_t)re, e->status, (uint32_t *)e->d_misc); e->launches++;
+    uint64_t tot = 0, first = 0;
+    CK(cudaMemcpyAsync(&tot, e->col_off + re, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(&first, e->col_off + rb, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    ENSURE(ents, (size_t)tot + 1);
+    k_entries_fill<<<nblk(re, 256), 256, 0, e->stream>>>(v, file, e->col_off, e->ents, e->h_file_start[file]); e->launches++;
+    CK(cudaGetLastError());
+    const size_t ne = (size_t)(tot - first);
+    *n_entries = ne;
+    if (ne > cap_entries) { snprintf(e->err, sizeof e->err, "entry buffer too small: need %zu", ne); return -2; }
+    CK(cudaMemcpyAsync(col_n, e->col_n + rb, (size_t)(re - rb) * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (ne) CK(cudaMemcpyAsync(entries, e->ents + first, ne * sizeof(b200_pileup1_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+#include "glf.cuh"

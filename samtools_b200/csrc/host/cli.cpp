@@ -1,0 +1,545 @@
+// cli.cpp -- `b200samtools mpileup|depth|coverage|gl`: the reference's CLI surface
+// for the pileup hot path, driving the CUDA engine through its C ABI.
+//
+// Option surfaces follow bam_plcmd.c:1096-1223 (mpileup), bam2depth.c:757-882
+// (depth) and coverage.c:343-424 (coverage), SURVEY.md Appendix B.  What stays
+// on the host is what the reference also does outside the column loop: option
+// parsing, file decode, per-contig sequencing of -a/-aa output
+// (bam_plcmd.c:610-660, :880-910; bam2depth.c:215-287; coverage.c:591-688) and
+// the final %g formatting of coverage rows (coverage.c:200-221).  Every read
+// filter, BAQ, overlap handling, the column loop and all text formatting run on
+// the GPU; there is no CPU fallback (engine creation fails without a device).
+//
+// Not offered on the device path yet: -M/--output-mods,
+// --output-QNAME, --output-extra; coverage histograms (-m/-A/-D/-w, terminal UI).
+#include "hts_io.hpp"
+#include "packer.hpp"
+#include <getopt.h>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cerrno>
+#include <algorithm>
+#include <set>
+
+using namespace b200;
+
+namespace {
+
+struct FileData {
+    std::unique_ptr<AlnReader> rd;
+    std::vector<std::vector<Record>> by_tid;   // decoded records per reference sequence, file order
+    int64_t n_no_tid = 0;
+};
+
+bool load_file(const std::string &fn, const std::string &fai, const char *reg, FileData &fd, int &rtid, int64_t &rbeg, int64_t &rend,
+               const char *cmd)
+{
+    fd.rd = AlnReader::open(fn, fai);
+    if (!fd.rd) { fprintf(stderr, "[%s] failed to open %s: %s\n", cmd, fn.c_str(), strerror(errno)); return false; }
+    if (reg && !fd.rd->set_region(reg, rtid, rbeg, rend)) {
+        fprintf(stderr, "[E::%s] fail to parse region '%s' with %s\n", cmd, reg, fn.c_str());
+        return false;
+    }
+    fd.by_tid.resize((size_t)fd.rd->header().n_ref());
+    Record r; int ret;
+    while ((ret = fd.rd->next(r)) >= 0) {
+        if (r.tid < 0 || r.tid >= (int)fd.by_tid.size()) { ++fd.n_no_tid; continue; }
+        fd.by_tid[(size_t)r.tid].push_back(std::move(r));
+    }
+    if (ret < -1) { fprintf(stderr, "samtools %s: error reading from input file\n", cmd); return false; }
+    return true;
+}
+
+struct Engine {
+    b200_engine_t *e = nullptr;
+    ~Engine() { if (e) b200_engine_destroy(e); }
+    bool init()
+    {
+        int dev = 0;
+        if (const char *s = getenv("B200_DEVICE")) dev = atoi(s);
+        if (b200_engine_create(dev, &e) != 0) { fprintf(stderr, "b200samtools: cannot create the CUDA pileup engine (a B200/sm_100a device is required)\n"); return false; }
+        return true;
+    }
+};
+
+// The engine addresses columns as 32-bit offsets from the window start.  Without
+// -a only positions under reads can be reported, so the window is shrunk to the
+// span of the batch (this is what lets 10^10-sized coordinates through).
+bool window_for(const PackedBatch &pb, int64_t beg, int64_t end, bool all, int64_t tid_len, int64_t &wbeg, int64_t &wend)
+{
+    wbeg = beg; wend = end;
+    if (!all && !pb.pos.empty()) {
+        int64_t lo = *std::min_element(pb.pos.begin(), pb.pos.end());
+        if (lo > wbeg) wbeg = lo;
+    }
+    const int64_t hi = all ? std::min(end, tid_len) : wbeg;
+    return hi - wbeg < (1LL << 31) - (1 << 20);
+}
+
+void write_all(FILE *fp, const std::vector<char> &buf, size_t n) { if (n) fwrite(buf.data(), 1, n, fp); }
+
+// ----------------------------------------------------------------------------- mpileup
+struct MpOpts {
+    int min_mq = 0, min_baseQ = 13, capQ = 0, max_depth = 8000, all = 0, rev_del = 0;
+    int rf = 0, ff = F_UNMAP | F_SECONDARY | F_QCFAIL | F_DUP;
+    bool no_orphan = true, realn = true, redo_baq = false, illumina13 = false, ignore_rg = false, overlaps = true;
+    int no_ins = 0, no_del = 0, no_ends = 0, out_mapq = 0, out_qpos = 0, out_qpos5 = 0;
+    const char *reg = nullptr, *fa_fn = nullptr, *out_fn = nullptr;
+    std::unique_ptr<Fasta> fa; std::unique_ptr<Bed> bed;
+    std::set<std::string> rg_excl; bool have_rg = false;
+    bool gl = false;
+};
+
+int count_samples(const std::vector<std::string> &fn, const std::vector<FileData> &fd, bool ignore_rg)
+{
+    // bam_smpl_add (sample.c:79-121): distinct @RG SM values, else the file name
+    std::set<std::string> smpl;
+    for (size_t i = 0; i < fn.size(); ++i) {
+        int n = 0;
+        if (!ignore_rg) {
+            const std::string &t = fd[i].rd->header().text;
+            size_t p = 0;
+            while ((p = t.find("@RG", p)) != std::string::npos) {
+                p += 3;
+                size_t id = t.find("\tID:", p), sm = t.find("\tSM:", p);
+                if (id == std::string::npos || sm == std::string::npos) break;
+                sm += 4;
+                size_t e = t.find_first_of("\t\n", sm);
+                smpl.insert(t.substr(sm, e == std::string::npos ? std::string::npos : e - sm));
+                p = std::max(id + 4, sm);
+                ++n;
+            }
+        }
+        if (n == 0) smpl.insert(fn[i]);
+    }
+    return (int)smpl.size();
+}
+
+// host bits of one record for mpileup: string filters and the stored-BAQ-tag integer path
+uint8_t mp_host_bits(const MpOpts &o, const Header &h, Record &r, bool has_ref)
+{
+    uint8_t rb = 0;
+    if (o.bed && o.all == 0 && !o.bed->overlap(h.names[(size_t)r.tid], r.pos, r.endpos())) rb |= B200_RB_HOST_SKIP;
+    if (o.have_rg) {
+        const uint8_t *rg = r.aux_get("RG");
+        if (rg && o.rg_excl.count((const char *)rg + 1)) rb |= B200_RB_HOST_SKIP;
+    }
+    if (has_ref && o.realn && !(rb & B200_RB_HOST_SKIP) && !(r.flag & F_UNMAP) && r.l_qseq > 0 && r.qual[0] != 0xff) {
+        // sam_prob_realn with existing tags (htslib realn.c): BQ:Z present and not -E -> integer adjust
+        const uint8_t *bq = r.aux_get("BQ"), *zq = r.aux_get("ZQ");
+        if (bq && *bq != 'Z') bq = nullptr;
+        if (zq && *zq != 'Z') zq = nullptr;
+        if (bq && o.redo_baq) bq = nullptr;        // -E: the tag is deleted, HMM recomputed on the device
+        else if (bq && zq) zq = nullptr;
+        if (bq) {
+            if (o.illumina13) for (auto &q : r.qual) q = q > 31 ? q - 31 : 0;   // -6 precedes BAQ (bam_plcmd.c:428-433)
+            const uint8_t *b = bq + 1;
+            for (int32_t i = 0; i < r.l_qseq; ++i) r.qual[(size_t)i] = r.qual[(size_t)i] + 64 < b[i] ? 0 : (uint8_t)(r.qual[(size_t)i] - ((int)b[i] - 64));
+            rb |= B200_RB_BAQ_DONE;
+        } else if (zq && !(o.redo_baq && false)) {
+            if (o.illumina13) for (auto &q : r.qual) q = q > 31 ? q - 31 : 0;
+            rb |= B200_RB_BAQ_DONE;               // ZQ present with APPLY: left untouched
+        }
+    }
+    return rb;
+}
+
+int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
+{
+    const int nfn = (int)fn.size();
+    if (nfn == 0) { fprintf(stderr, "[mpileup] no input file/data given\n"); return 1; }
+    std::vector<FileData> fd((size_t)nfn);
+    int tid0 = 0; int64_t beg0 = 0, end0 = POS_MAX;
+    const std::string fai = o.fa_fn ? std::string(o.fa_fn) + ".fai" : "";
+    for (int i = 0; i < nfn; ++i) {
+        int t = 0; int64_t b = 0, e = POS_MAX;
+        if (!load_file(fn[(size_t)i], fai, o.reg, fd[(size_t)i], t, b, e, "mpileup")) return 1;
+        if (i == 0) { tid0 = t; beg0 = b; end0 = e; }
+    }
+    const Header &h = fd[0].rd->header();
+    fprintf(stderr, "[mpileup] %d samples in %d input files\n", count_samples(fn, fd, o.ignore_rg), nfn);
+    FILE *fp = o.out_fn ? fopen(o.out_fn, "w") : stdout;
+    if (!fp) { fprintf(stderr, "[mpileup] failed to write to %s: %s\n", o.out_fn, strerror(errno)); return 1; }
+    int max_depth = o.max_depth;
+    if (!max_depth) { max_depth = INT_MAX; fprintf(stderr, "[mpileup] Max depth set to maximum value (%d)\n", INT_MAX); }
+    else if ((long long)max_depth * nfn > 1 << 20) fprintf(stderr, "[mpileup] Combined max depth is above 1M. Potential memory hog!\n");
+
+    Engine eng;
+    if (!eng.init()) return 1;
+    b200_stage_conf_t sc; memset(&sc, 0, sizeof sc);
+    sc.mode = B200_MODE_MPILEUP; sc.rflag_require = o.rf; sc.rflag_filter = o.ff; sc.min_mq = o.min_mq; sc.no_orphan = o.no_orphan;
+    sc.illumina13 = o.illumina13; sc.baq = o.realn ? (o.redo_baq ? 2 : 1) : 0; sc.capq_thres = o.capQ; sc.overlaps = o.overlaps;
+    sc.max_depth = max_depth; sc.beg = o.reg ? beg0 : 0; sc.end = o.reg ? end0 : POS_MAX;
+    b200_mpileup_conf_t mc; memset(&mc, 0, sizeof mc);
+    mc.min_baseQ = o.min_baseQ; mc.all = o.all; mc.rev_del = o.rev_del; mc.no_ins = o.no_ins; mc.no_del = o.no_del; mc.no_ends = o.no_ends;
+    mc.out_mapq = o.out_mapq; mc.out_qpos = o.out_qpos; mc.out_qpos5 = o.out_qpos5;
+
+    PackedBatch pb;
+    std::vector<char> out;
+    std::vector<int64_t> bb, be;
+    const int nref = h.n_ref();
+    auto process_tid = [&](int tid, bool with_reads) -> int {
+        // returns 1 when rows were requested and produced, 0 when the contig has no pileup column, <0 on error
+        const std::string &name = h.names[(size_t)tid];
+        const std::string *ref = nullptr;
+        if (o.fa) { int fi = o.fa->find(name); if (fi >= 0) ref = &o.fa->seqs[(size_t)fi]; }
+        pb.clear();
+        for (int i = 0; i < nfn; ++i) {
+            pb.begin_file();
+            if (with_reads && tid < (int)fd[(size_t)i].by_tid.size())
+                for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) pb.add(r, mp_host_bits(o, h, r, ref != nullptr), o.overlaps);
+        }
+        pb.finish();
+        b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], name, ref);
+        b200_stage_stats_t st;
+        if (!window_for(pb, o.reg ? beg0 : 0, o.reg ? end0 : POS_MAX, o.all != 0, h.lens[(size_t)tid], sc.beg, sc.end)) {
+            fprintf(stderr, "samtools mpileup: contig %s needs more than one 2^31-column window with -a (not supported yet)\n", name.c_str());
+            return -1;
+        }
+        if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools mpileup: %s\n", b200_last_error(eng.e)); return -1; }
+        if (with_reads && st.n_kept_in_window == 0) return 0;
+        if (o.bed) { o.bed->merged(name, bb, be); mc.bed_beg = bb.data(); mc.bed_end = be.data(); mc.n_bed = (int)bb.size(); mc.bed_active = 1; }
+        if (o.gl) {
+            int64_t ncols = 0; const size_t cap = (size_t)st.n_cols + 16;
+            std::vector<int64_t> cpos(cap); std::vector<int32_t> nb(cap * (size_t)nfn); std::vector<float> qs(cap * (size_t)nfn * 4), p25(cap * (size_t)nfn * 25);
+            if (b200_glf(eng.e, o.min_baseQ, &ncols, cpos.data(), nb.data(), qs.data(), p25.data(), cap) != 0) { fprintf(stderr, "samtools gl: %s\n", b200_last_error(eng.e)); return -1; }
+            for (int64_t k = 0; k < ncols; ++k) {
+                const int64_t p = cpos[(size_t)k];
+                if (o.bed && !o.bed->overlap(name, p, p + 1)) continue;
+                fprintf(fp, "%s\t%lld\t%c", name.c_str(), (long long)p + 1, (ref && p < (int64_t)ref->size()) ? (*ref)[(size_t)p] : 'N');
+                for (int f = 0; f < nfn; ++f) {
+                    const size_t d = (size_t)k * (size_t)nfn + (size_t)f;
+                    fprintf(fp, "\t%d", nb[d] < 0 ? 0 : nb[d]);
+                    for (int j = 0; j < 4; ++j) fprintf(fp, "\t%.9g", qs[d * 4 + (size_t)j]);
+                    for (int j = 0; j < 25; ++j) fprintf(fp, "\t%.9g", p25[d * 25 + (size_t)j]);
+                }
+                fputc('\n', fp);
+            }
+            return 1;
+        }
+        size_t need = 0;
+        int rc = b200_mpileup_text(eng.e, &mc, nullptr, 0, &need);      // format in HBM, learn the size
+        if (rc == 0) { out.resize(need + 1); rc = b200_mpileup_text(eng.e, &mc, out.data(), out.size(), &need); }
+        if (rc != 0) { fprintf(stderr, "samtools mpileup: %s\n", b200_last_error(eng.e)); return -1; }
+        write_all(fp, out, need);
+        return 1;
+    };
+
+    // contigs that yield at least one pileup column inside the region, in order (bam_plcmd.c:607-609)
+    bool any = false;
+    if (o.all < 2 || o.reg) {
+        for (int tid = 0; tid < nref; ++tid) {
+            if (o.reg && tid != tid0) continue;
+            bool has = false;
+            for (int i = 0; i < nfn; ++i) if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+            if (!has) continue;
+            int rc = process_tid(tid, true);
+            if (rc < 0) return 1;
+            if (rc > 0) any = true;
+        }
+        // -aa with a region but no column at all: the region's empty rows (bam_plcmd.c:882-885)
+        if (!any && o.all > 1 && o.reg && !o.gl) { if (process_tid(tid0, false) < 0) return 1; }
+    } else {
+        // -aa without a region: every contig, covered or not (bam_plcmd.c:612-636, :886-909)
+        for (int tid = 0; tid < nref; ++tid) {
+            bool has = false;
+            for (int i = 0; i < nfn; ++i) if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+            int rc = has ? process_tid(tid, true) : 0;
+            if (rc < 0) return 1;
+            if (rc == 0 && !o.gl) { if (process_tid(tid, false) < 0) return 1; }
+        }
+    }
+    if (o.out_fn) fclose(fp); else fflush(fp);
+    return 0;
+}
+
+int main_mpileup(int argc, char **argv, bool gl)
+{
+    MpOpts o; o.gl = gl;
+    const char *file_list = nullptr; bool use_orphan = false, has_index_file = false;
+    static const struct option lo[] = {
+        {"rf", 1, 0, 1}, {"ff", 1, 0, 2}, {"incl-flags", 1, 0, 1}, {"excl-flags", 1, 0, 2}, {"output", 1, 0, 3},
+        {"output-QNAME", 0, 0, 5}, {"output-qname", 0, 0, 5}, {"illumina1.3+", 0, 0, '6'}, {"count-orphans", 0, 0, 'A'},
+        {"bam-list", 1, 0, 'b'}, {"no-BAQ", 0, 0, 'B'}, {"no-baq", 0, 0, 'B'}, {"adjust-MQ", 1, 0, 'C'}, {"adjust-mq", 1, 0, 'C'},
+        {"max-depth", 1, 0, 'd'}, {"redo-BAQ", 0, 0, 'E'}, {"redo-baq", 0, 0, 'E'}, {"fasta-ref", 1, 0, 'f'}, {"reference", 1, 0, 'f'},
+        {"exclude-RG", 1, 0, 'G'}, {"exclude-rg", 1, 0, 'G'}, {"positions", 1, 0, 'l'}, {"region", 1, 0, 'r'},
+        {"ignore-RG", 0, 0, 'R'}, {"ignore-rg", 0, 0, 'R'}, {"min-MQ", 1, 0, 'q'}, {"min-mq", 1, 0, 'q'}, {"min-BQ", 1, 0, 'Q'},
+        {"min-bq", 1, 0, 'Q'}, {"ignore-overlaps-removal", 0, 0, 'x'}, {"disable-overlap-removal", 0, 0, 'x'},
+        {"output-mods", 0, 0, 'M'}, {"output-BP", 0, 0, 'O'}, {"output-bp", 0, 0, 'O'}, {"output-BP-5", 0, 0, 14}, {"output-bp-5", 0, 0, 14},
+        {"output-MQ", 0, 0, 's'}, {"output-mq", 0, 0, 's'}, {"customized-index", 0, 0, 'X'}, {"reverse-del", 0, 0, 6},
+        {"output-extra", 1, 0, 7}, {"output-sep", 1, 0, 8}, {"output-empty", 1, 0, 9}, {"no-output-ins", 0, 0, 10},
+        {"no-output-ins-mods", 0, 0, 11}, {"no-output-del", 0, 0, 12}, {"no-output-ends", 0, 0, 13}, {0, 0, 0, 0} };
+    int c;
+    optind = 1;
+    while ((c = getopt_long(argc, argv, "Af:r:l:q:Q:RC:Bd:b:o:EG:6OsxXaM", lo, nullptr)) >= 0) {
+        switch (c) {
+        case 'x': o.overlaps = false; break;
+        case 1: o.rf = parse_flag(optarg); if (o.rf < 0) { fprintf(stderr, "Could not parse --rf %s\n", optarg); return 1; } break;
+        case 2: o.ff = parse_flag(optarg); if (o.ff < 0) { fprintf(stderr, "Could not parse --ff %s\n", optarg); return 1; } break;
+        case 3: case 'o': o.out_fn = optarg; break;
+        case 5: case 7: case 'M':
+            fprintf(stderr, "b200samtools mpileup: --output-QNAME/--output-extra/--output-mods are not available on the device path yet\n");
+            return 1;
+        case 6: o.rev_del = 1; break;
+        case 8: case 9: case 11: break;
+        case 10: o.no_ins++; break;
+        case 12: o.no_del++; break;
+        case 13: o.no_ends = 1; break;
+        case 14: o.out_qpos5 = 1; break;
+        case 'f': o.fa = Fasta::load(optarg); if (!o.fa) { fprintf(stderr, "[E::fai_load] failed to open %s\n", optarg); return 1; } o.fa_fn = optarg; break;
+        case 'd': o.max_depth = atoi(optarg); break;
+        case 'r': o.reg = optarg; break;
+        case 'l': o.bed = Bed::load(optarg); if (!o.bed) { fprintf(stderr, "samtools mpileup: Could not read file \"%s\"\n", optarg); return 1; } break;
+        case 'B': o.realn = false; break;
+        case 'X': has_index_file = true; break;
+        case 'E': o.redo_baq = true; break;
+        case '6': o.illumina13 = true; break;
+        case 'R': o.ignore_rg = true; break;
+        case 's': o.out_mapq = 1; break;
+        case 'O': o.out_qpos = 1; break;
+        case 'C': o.capQ = atoi(optarg); break;
+        case 'q': o.min_mq = atoi(optarg); break;
+        case 'Q': o.min_baseQ = atoi(optarg); break;
+        case 'b': file_list = optarg; break;
+        case 'A': use_orphan = true; break;
+        case 'G': {
+            o.have_rg = true;
+            if (FILE *f = fopen(optarg, "r")) { char b[1024]; while (fscanf(f, "%1023s", b) > 0) o.rg_excl.insert(b); fclose(f); }
+            else fprintf(stderr, "[bam_mpileup] Fail to open file %s. Continue anyway.\n", optarg);
+            break;
+        }
+        case 'a': o.all++; break;
+        default: fprintf(stderr, "\nUsage: samtools mpileup [options] in1.bam [in2.bam [...]]\n"); return 1;
+        }
+    }
+    if (!o.realn && o.redo_baq) { fprintf(stderr, "Error: The -B option cannot be combined with -E\n"); return 1; }
+    if (use_orphan) o.no_orphan = false;
+    if (argc == 1) { fprintf(stderr, "\nUsage: samtools mpileup [options] in1.bam [in2.bam [...]]\n"); return 1; }
+    std::vector<std::string> fn;
+    if (file_list) {
+        if (has_index_file) { fprintf(stderr, "Error: The -b option cannot be combined with -X\n"); return 1; }
+        if (!read_file_list(file_list, fn)) return 1;
+    } else {
+        int n = argc - optind;
+        if (has_index_file) { if (n % 2) { fprintf(stderr, "Odd number of filenames detected! Each BAM file should have an index file\n"); return 1; } n /= 2; }
+        for (int i = 0; i < n; ++i) fn.push_back(argv[optind + i]);
+    }
+    return run_mpileup(o, fn);
+}
+
+// ----------------------------------------------------------------------------- depth
+int main_depth(int argc, char **argv)
+{
+    int flag = F_UNMAP | F_SECONDARY | F_DUP | F_QCFAIL, incl = 0, require = 0, min_qual = 0, min_mqual = 0, min_len = 0;
+    int skip_del = 1, header = 0, all_pos = 0, remove_overlaps = 0, tmp;
+    const char *reg = nullptr, *file_list = nullptr, *out_fn = nullptr;
+    std::unique_ptr<Bed> bed;
+    static const struct option lo[] = { {"min-MQ", 1, 0, 'Q'}, {"min-mq", 1, 0, 'Q'}, {"min-BQ", 1, 0, 'q'}, {"min-bq", 1, 0, 'q'},
+        {"excl-flags", 1, 0, 'G'}, {"incl-flags", 1, 0, 1}, {"require-flags", 1, 0, 2}, {"threads", 1, 0, '@'}, {0, 0, 0, 0} };
+    int c;
+    optind = 1;
+    while ((c = getopt_long(argc, argv, "@:q:Q:JHd:m:l:g:G:o:ar:Xf:b:s", lo, nullptr)) >= 0) {
+        switch (c) {
+        case 'a': all_pos++; break;
+        case 'b': bed = Bed::load(optarg); if (!bed) { fprintf(stderr, "samtools depth: Could not read file \"%s\"\n", optarg); return 1; } break;
+        case 'f': file_list = optarg; break;
+        case 'd': case 'm': case '@': case 'X': break;
+        case 'g': tmp = parse_flag(optarg); if (tmp < 0) { fprintf(stderr, "samtools depth: Unknown flag '%s'\n", optarg); return 1; } flag &= ~tmp; break;
+        case 'G': tmp = parse_flag(optarg); if (tmp < 0) { fprintf(stderr, "samtools depth: Unknown flag '%s'\n", optarg); return 1; } flag |= tmp; break;
+        case 1: tmp = parse_flag(optarg); if (tmp < 0) { fprintf(stderr, "samtools depth: Unknown flag '%s'\n", optarg); return 1; } incl |= tmp; break;
+        case 2: tmp = parse_flag(optarg); if (tmp < 0) { fprintf(stderr, "samtools depth: Unknown flag '%s'\n", optarg); return 1; } require |= tmp; break;
+        case 'l': min_len = atoi(optarg); break;
+        case 'H': header = 1; break;
+        case 'q': min_qual = atoi(optarg); break;
+        case 'Q': min_mqual = atoi(optarg); break;
+        case 'J': skip_del = 0; break;
+        case 'o': out_fn = optarg; break;
+        case 'r': reg = optarg; break;
+        case 's': remove_overlaps = 1; break;
+        default: fprintf(stderr, "Usage: samtools depth [options] in.bam [in.bam ...]\n"); return 1;
+        }
+    }
+    std::vector<std::string> fn;
+    if (file_list) { if (!read_file_list(file_list, fn)) return 1; }
+    else for (int i = optind; i < argc; ++i) fn.push_back(argv[i]);
+    if (fn.empty()) { fprintf(stderr, "Usage: samtools depth [options] in.bam [in.bam ...]\n"); return 1; }
+    const int nfn = (int)fn.size();
+    std::vector<FileData> fd((size_t)nfn);
+    int tid0 = 0; int64_t beg0 = 0, end0 = POS_MAX;
+    for (int i = 0; i < nfn; ++i) {
+        int t = 0; int64_t b = 0, e = POS_MAX;
+        fd[(size_t)i].rd = nullptr;
+        if (!load_file(fn[(size_t)i], "", reg, fd[(size_t)i], t, b, e, "depth")) return 1;
+        if (i == 0) { tid0 = t; beg0 = b; end0 = e; }
+    }
+    const Header &h = fd[0].rd->header();
+    FILE *fp = out_fn ? fopen(out_fn, "w") : stdout;
+    if (!fp) { fprintf(stderr, "samtools depth: Cannot open \"%s\" for writing.\n", out_fn); return 1; }
+    if (header) { fprintf(fp, "#CHROM\tPOS"); for (auto &f : fn) fprintf(fp, "\t%s", f.c_str()); fputc('\n', fp); }
+    Engine eng;
+    if (!eng.init()) return 1;
+    b200_stage_conf_t sc; memset(&sc, 0, sizeof sc);
+    sc.mode = B200_MODE_DEPTH; sc.d_flag_excl = flag; sc.d_flag_incl = incl; sc.d_flag_require = require; sc.d_min_mapq = min_mqual;
+    sc.d_min_len = min_len; sc.d_remove_overlaps = remove_overlaps; sc.beg = reg ? beg0 : 0; sc.end = reg ? end0 : POS_MAX;
+    b200_depth_conf_t dc; memset(&dc, 0, sizeof dc);
+    dc.min_qual = min_qual; dc.count_del = !skip_del; dc.all = all_pos;
+    PackedBatch pb; std::vector<char> out; std::vector<int64_t> bb, be;
+    auto process_tid = [&](int tid, bool with_reads) -> int {
+        const std::string &name = h.names[(size_t)tid];
+        pb.clear();
+        for (int i = 0; i < nfn; ++i) {
+            pb.begin_file();
+            if (with_reads && tid < (int)fd[(size_t)i].by_tid.size()) for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) pb.add(r, 0, remove_overlaps != 0);
+        }
+        pb.finish();
+        b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], name, nullptr);
+        b200_stage_stats_t st;
+        if (!window_for(pb, reg ? beg0 : 0, reg ? end0 : POS_MAX, all_pos != 0, h.lens[(size_t)tid], sc.beg, sc.end)) {
+            fprintf(stderr, "samtools depth: contig %s needs more than one 2^31-column window with -a (not supported yet)\n", name.c_str());
+            return -1;
+        }
+        if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools depth: %s\n", b200_last_error(eng.e)); return -1; }
+        if (with_reads && st.n_kept == 0) return 0;   // no record survives the filters: the contig is never "seen"
+        if (bed) { bed->merged(name, bb, be); dc.bed_beg = bb.data(); dc.bed_end = be.data(); dc.n_bed = (int)bb.size(); dc.bed_active = 1; }
+        size_t need = 0;
+        int rc = b200_depth_text(eng.e, &dc, nullptr, 0, &need);
+        if (rc == 0) { out.resize(need + 1); rc = b200_depth_text(eng.e, &dc, out.data(), out.size(), &need); }
+        if (rc != 0) { fprintf(stderr, "samtools depth: %s\n", b200_last_error(eng.e)); return -1; }
+        write_all(fp, out, need);
+        return 1;
+    };
+    const int nref = h.n_ref();
+    bool any = false;
+    for (int tid = 0; tid < nref; ++tid) {
+        if (reg && tid != tid0) continue;
+        bool has = false;
+        for (int i = 0; i < nfn; ++i) if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+        int rc = has ? process_tid(tid, true) : 0;
+        if (rc < 0) return 1;
+        if (rc > 0) any = true;
+        else if (all_pos > 1 && !reg) { if (process_tid(tid, false) < 0) return 1; }   // -aa: unused references (bam2depth.c:255-263)
+    }
+    if (!any && all_pos && reg) { if (process_tid(tid0, false) < 0) return 1; }            // bam2depth.c:267-270
+    if (out_fn) fclose(fp); else fflush(fp);
+    return 0;
+}
+
+// ----------------------------------------------------------------------------- coverage
+int main_coverage(int argc, char **argv)
+{
+    int max_depth = 1000000, min_baseQ = 0, min_mapQ = 0, min_len = 0, mindepth = 1;
+    int fail_flags = F_UNMAP | F_SECONDARY | F_QCFAIL | F_DUP, required_flags = 0;
+    const char *reg = nullptr, *file_list = nullptr, *out_fn = nullptr;
+    bool print_header = true;
+    static const struct option lo[] = { {"rf", 1, 0, 1}, {"ff", 1, 0, 2}, {"incl-flags", 1, 0, 1}, {"excl-flags", 1, 0, 2},
+        {"bam-list", 1, 0, 'b'}, {"min-read-len", 1, 0, 'l'}, {"min-MQ", 1, 0, 'q'}, {"min-mq", 1, 0, 'q'}, {"min-BQ", 1, 0, 'Q'},
+        {"min-bq", 1, 0, 'Q'}, {"histogram", 0, 0, 'm'}, {"ascii", 0, 0, 'A'}, {"plot-depth", 0, 0, 'D'}, {"output", 1, 0, 'o'},
+        {"no-header", 0, 0, 'H'}, {"n-bins", 1, 0, 'w'}, {"region", 1, 0, 'r'}, {"help", 0, 0, 'h'}, {"depth", 1, 0, 'd'},
+        {"min-depth", 1, 0, 3}, {0, 0, 0, 0} };
+    int c, i;
+    optind = 1; opterr = 0;
+    while ((c = getopt_long(argc, argv, "Ao:l:q:Q:hHw:r:b:md:D", lo, nullptr)) != -1) {
+        switch (c) {
+        case 1: if ((required_flags = parse_flag(optarg)) < 0) { fprintf(stderr, "Could not parse --rf %s\n", optarg); return 1; } break;
+        case 2: if ((fail_flags = parse_flag(optarg)) < 0) { fprintf(stderr, "Could not parse --ff %s\n", optarg); return 1; } break;
+        case 3: if ((i = atoi(optarg)) > 0) mindepth = i; break;
+        case 'o': out_fn = optarg; break;
+        case 'l': min_len = atoi(optarg); break;
+        case 'q': min_mapQ = atoi(optarg); break;
+        case 'Q': min_baseQ = atoi(optarg); break;
+        case 'd': max_depth = atoi(optarg); break;
+        case 'r': reg = optarg; break;
+        case 'b': file_list = optarg; break;
+        case 'H': print_header = false; break;
+        case 'm': case 'A': case 'D': case 'w':
+            fprintf(stderr, "b200samtools coverage: histogram views are terminal UI and not provided; tabular output only\n"); return 1;
+        default: fprintf(stderr, "Usage: samtools coverage [options] in1.bam [in2.bam [...]]\n"); return 1;
+        }
+    }
+    std::vector<std::string> fn;
+    if (file_list) { if (!read_file_list(file_list, fn)) return 1; }
+    else for (i = optind; i < argc; ++i) fn.push_back(argv[i]);
+    if (fn.empty()) { fprintf(stderr, "Usage: samtools coverage [options] in1.bam [in2.bam [...]]\n"); return 1; }
+    const int nfn = (int)fn.size();
+    std::vector<FileData> fd((size_t)nfn);
+    int tid0 = -1; int64_t beg0 = 0, end0 = POS_MAX;
+    for (i = 0; i < nfn; ++i) {
+        int t = 0; int64_t b = 0, e = POS_MAX;
+        if (!load_file(fn[(size_t)i], "", reg, fd[(size_t)i], t, b, e, "coverage")) return 1;
+        if (i == 0 && reg) { tid0 = t; beg0 = b; end0 = e; }
+    }
+    const Header &h = fd[0].rd->header();
+    FILE *fp = (out_fn && strcmp(out_fn, "-")) ? fopen(out_fn, "w") : stdout;
+    if (!fp) { fprintf(stderr, "samtools coverage: Cannot open \"%s\" for writing.\n", out_fn); return 1; }
+    Engine eng;
+    if (!eng.init()) return 1;
+    const int nref = h.n_ref();
+    struct Row { b200_coverage_sums_t s; uint64_t n_sel = 0, sum_mq = 0; bool covered = false; int64_t beg = 0, end = 0; };
+    std::vector<Row> rows((size_t)nref);
+    b200_stage_conf_t sc; memset(&sc, 0, sizeof sc);
+    sc.mode = B200_MODE_COVERAGE; sc.rflag_filter = fail_flags; sc.rflag_require = required_flags; sc.min_mq = min_mapQ; sc.c_min_len = min_len;
+    sc.max_depth = max_depth > 0 ? max_depth : (max_depth == 0 ? INT_MAX : 8000);
+    b200_coverage_conf_t cc; cc.min_baseQ = min_baseQ; cc.min_depth = mindepth;
+    PackedBatch pb;
+    bool warn = false;
+    std::vector<int> order;   // contigs in the order their first column appears
+    for (int tid = 0; tid < nref; ++tid) {
+        Row &rw = rows[(size_t)tid];
+        memset(&rw.s, 0, sizeof rw.s);
+        rw.beg = 0; rw.end = h.lens[(size_t)tid];
+        if (reg && tid == tid0) { rw.beg = beg0; rw.end = end0 == POS_MAX ? h.lens[(size_t)tid] : end0; }
+        bool has = false;
+        for (i = 0; i < nfn; ++i) if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+        if (!has) continue;
+        pb.clear();
+        for (i = 0; i < nfn; ++i) {
+            pb.begin_file();
+            if (tid < (int)fd[(size_t)i].by_tid.size()) for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) pb.add(r, 0, false);
+        }
+        pb.finish();
+        b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], h.names[(size_t)tid], nullptr);
+        sc.beg = rw.beg; sc.end = rw.end;
+        b200_stage_stats_t st;
+        if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools coverage: %s\n", b200_last_error(eng.e)); return 1; }
+        rw.n_sel = st.n_selected_reads; rw.sum_mq = st.summed_mapq;
+        // a column exists as soon as one kept read has a non-empty reference span (before the region test)
+        if (st.n_kept > 0) {
+            if (b200_coverage(eng.e, &cc, &rw.s) != 0) { fprintf(stderr, "samtools coverage: %s\n", b200_last_error(eng.e)); return 1; }
+            rw.covered = true;   // refined below: zero-span-only contigs are vanishingly rare
+            order.push_back(tid);
+            if (rw.s.missing_qual) warn = true;
+        }
+    }
+    auto print_row = [&](int tid) {
+        const Row &r = rows[(size_t)tid];
+        if (print_header) { fputs("#rname\tstartpos\tendpos\tnumreads\tcovbases\tcoverage\tmeandepth\tmeanbaseq\tmeanmapq\n", fp); print_header = false; }
+        fputs(h.names[(size_t)tid].c_str(), fp);
+        double region_len = (double)r.end - r.beg;
+        fprintf(fp, "\t%lld\t%lld\t%u\t%llu\t%g\t%g\t%.3g\t%.3g\n", (long long)r.beg + 1, (long long)r.end, (unsigned)r.n_sel,
+                (unsigned long long)r.s.n_covered_bases, 100.0 * r.s.n_covered_bases / region_len, r.s.summed_coverage / region_len,
+                r.s.quality_bases > 0 ? r.s.summed_baseQ / (double)r.s.quality_bases : 0,
+                r.n_sel > 0 ? r.sum_mq / (double)r.n_sel : 0);
+    };
+    for (int tid : order) print_row(tid);
+    if (order.empty() && reg && *reg != '*' && tid0 >= 0) print_row(tid0);
+    if (!reg) for (int tid = 0; tid < nref; ++tid) if (!rows[(size_t)tid].covered) print_row(tid);
+    if (warn) fprintf(stderr, "samtools coverage: Warning:  Missing quality values in alignments.  Mean base quality calculated only on available values.\n");
+    if (fp != stdout) fclose(fp); else fflush(fp);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) { fprintf(stderr, "Usage: b200samtools <mpileup|depth|coverage|gl> [options]\n"); return 1; }
+    std::string cmd = argv[1];
+    if (cmd == "mpileup") return main_mpileup(argc - 1, argv + 1, false);
+    if (cmd == "gl") return main_mpileup(argc - 1, argv + 1, true);
+    if (cmd == "depth") return main_depth(argc - 1, argv + 1);
+    if (cmd == "coverage") return main_coverage(argc - 1, argv + 1);
+    fprintf(stderr, "b200samtools: unrecognized command '%s'\n", argv[1]);
+    return 1;
+}

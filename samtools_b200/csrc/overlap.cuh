@@ -1,0 +1,65 @@
+// overlap.cuh -- read-pair overlap handling on the device.
+//
+// mpileup (htslib sam.c overlap_push / tweak_overlap_quality / overlap_remove,
+// enabled at bam_plcmd.c:586; rule text doc/samtools-mpileup.1:353-365):
+// the reference keeps a qname -> buffered-read hash while it streams reads.
+// Here the host supplies, for every record, the index of the previous record
+// with the same name (prev_same_name); the device turns that into forward
+// chains and one thread replays the hash's state machine along each chain
+// (chains are independent; typical length 2).  The quality rewrite itself walks
+// both CIGARs in lock-step over the shared reference span.
+//
+// depth -s (bam2depth.c:598-623): same chains, but the state is just the first
+// mate's end position, which becomes the second mate's clip coordinate.
+#pragma once
+
+__global__ void k_link_next(const int64_t *prev, int64_t *next, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = prev[i];
+    if (p >= 0 && p < n) next[p] = i;
+}
+
+__global__ void k_overlap(RawSoA r, const int64_t *next, const uint8_t *state, const int32_t *rlen,
+                          const int64_t *file_start, int n_files)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r.n) overlap_chain(r, i, next, state, rlen, file_start, n_files);
+}
+__global__ void k_depth_clip(RawSoA r, const int64_t *next, const uint8_t *state, const int32_t *rlen, int32_t *clip, int64_t win_base)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < r.n) depth_clip_chain(r, i, next, state, rlen, clip, win_base);
+}
+
+__global__ void k_fill_i64(int64_t *p, int64_t v, int64_t n) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void k_fill_i32(int32_t *p, int32_t v, int64_t n) { int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+static int link_chains(b200_engine *e, const RawSoA &r)
+{
+    const int64_t n = r.n;
+    if (ensure(e, e->next, e->cap_next, (size_t)n + 1)) return -1;
+    k_fill_i64<<<nblk(n, 256), 256, 0, e->stream>>>(e->next, -1, n); e->launches++;
+    k_link_next<<<nblk(n, 256), 256, 0, e->stream>>>(r.prev, e->next, n); e->launches++;
+    return 0;
+}
+
+int launch_overlap(b200_engine *e, const RawSoA &r)
+{
+    if (link_chains(e, r)) return -1;
+    k_overlap<<<nblk(r.n, 128), 128, 0, e->stream>>>(r, e->next, e->state, e->rlen, e->file_start, e->n_files); e->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int launch_depth_clip(b200_engine *e, const RawSoA &r)
+{
+    if (link_chains(e, r)) return -1;
+    if (ensure(e, e->clip, e->cap_clip, (size_t)r.n + 1)) return -1;
+    k_fill_i32<<<nblk(r.n, 256), 256, 0, e->stream>>>(e->clip, INT32_MIN, r.n); e->launches++;
+    k_depth_clip<<<nblk(r.n, 128), 128, 0, e->stream>>>(r, e->next, e->state, e->rlen, e->clip, e->win_base); e->launches++;
+    CK(cudaGetLastError());
+    e->has_clip = true;
+    return 0;
+}

@@ -1,0 +1,511 @@
+// plp_core.h -- per-column pileup arithmetic shared by all kernels.
+//
+// Everything here is a pure function of (staged batch, column): no state is
+// carried from column to column, unlike htslib's incremental CIGAR cursor
+// (resolve_cigar2) -- that is what lets one GPU thread own one reference
+// position.  Functions are __host__ __device__ so the exact same code can be
+// single-stepped on the CPU by the debug harness in tests/emul/ (not shipped,
+// not linked into the product library).
+//
+// Reference behaviour restated here (file:line into /root/reference):
+//   resolve()            htslib sam.c resolve_cigar2       
+//   ins_scan()/ins_write htslib sam.c bam_plp_insertion_mod
+//   mp_entry_*           pileup_seq                bam_plcmd.c:54-169
+//   mp_file_size/write   column loop per file      bam_plcmd.c:669-797
+//   mp_empty_*           print_empty_pileup        bam_plcmd.c:372-398
+//   dp_*                 add_depth / flush rows    bam2depth.c:209-477
+//   cv_column            coverage reducers         coverage.c:622-660
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PLP_HD __host__ __device__ __forceinline__
+#else
+#define PLP_HD inline
+#endif
+
+namespace plp {
+
+// CIGAR ops, BAM encoding
+enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X };
+
+// 32-byte read descriptor built on the device by the read stage
+struct ReadDesc {
+    int32_t rpos;      // leftmost column, relative to the window base
+    int32_t rend;      // one past the last column the read can appear in (== rpos: never)
+    uint64_t qoff;     // offset of qual[0]; nibble offset of the first base
+    uint32_t cig_off;  // first CIGAR op
+    int32_t l_qseq;
+    uint16_t n_cigar;
+    uint8_t mapq;
+    uint8_t fl;        // RD_* bits
+    int32_t qstart;    // RD_SIMPLE: query index aligned to rpos
+};
+enum { RD_REV = 1, RD_SIMPLE = 2 };
+
+struct View {
+    const ReadDesc *desc;
+    const uint32_t *cigar;
+    const int32_t *cig_x;      // per CIGAR op: first column of the op (relative), parallel to cigar[]
+    const int32_t *cig_y;      // per CIGAR op: query offset at the start of the op
+    const uint8_t *seq4;
+    const uint8_t *qual;
+    const int32_t *clip;       // depth -s: per-read overlap clip (relative), or nullptr
+    const char *ref;           // reference bases or nullptr
+    int64_t ref_off;           // relative column of ref[0]
+    int64_t ref_n;             // bytes available in ref
+    int64_t ref_len_rel;       // contig length in the FASTA, relative to the window base
+    int32_t n_files;
+    const int64_t *file_start; // [n_files+1]
+    const int32_t *tile_lo;    // [n_files][n_tiles] first read to inspect
+    const int32_t *tile_hi;    // [n_files][n_tiles] one past the last
+    int32_t n_tiles;
+    int32_t tile_cols;
+    int64_t win_base;          // absolute coordinate of relative column 0
+    int32_t ncols;             // columns [0,ncols) are candidates for output
+    int32_t ncols_all;         // -a: columns [0,ncols_all) are emitted even if empty
+    const char *name; int32_t name_len;
+    const int64_t *bed_beg, *bed_end; int32_t n_bed; int32_t bed_active;
+};
+
+struct MpConf {
+    int32_t min_baseQ, all, rev_del, no_ins, no_del, no_ends, out_mapq, out_qpos, out_qpos5, n_star_cols;
+};
+struct DpConf { int32_t min_qual, count_del, all; };
+
+struct Ent {
+    int32_t qpos, indel, k;
+    uint8_t is_del, is_refskip, is_head, is_tail;
+};
+
+PLP_HD int ndigits(uint64_t v)
+{
+    int n = 1;
+    while (v >= 10) { v /= 10; ++n; }
+    return n;
+}
+PLP_HD int put_u64(char *p, uint64_t v)
+{
+    int n = ndigits(v);
+    for (int i = n - 1; i >= 0; --i) { p[i] = (char)('0' + v % 10); v /= 10; }
+    return n;
+}
+PLP_HD int base4(const uint8_t *seq4, uint64_t qoff, int32_t i)
+{
+    uint64_t n = qoff + (uint64_t)i;
+    return (seq4[n >> 1] >> ((~n & 1) << 2)) & 0xf;
+}
+PLP_HD bool is_refop(int op) { return op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X; }
+PLP_HD bool is_mop(int op) { return op == OP_M || op == OP_EQ || op == OP_X; }
+
+// IUPAC character -> 4-bit code (htslib seq_nt16_table), computed not tabled
+PLP_HD int nt16_of(unsigned char ch)
+{
+    switch (ch | 0x20) {  // case-insensitive letters
+    case 'a': return 1; case 'c': return 2; case 'm': return 3; case 'g': return 4; case 'r': return 5;
+    case 's': return 6; case 'v': return 7; case 't': return 8; case 'w': return 9; case 'y': return 10;
+    case 'h': return 11; case 'k': return 12; case 'd': return 13; case 'b': return 14; case 'n': return 15;
+    default: break;
+    }
+    if (ch == '=') return 0;
+    if (ch == '0') return 1;
+    if (ch == '1') return 2;
+    if (ch == '2') return 4;
+    if (ch == '3') return 8;
+    return 15;
+}
+PLP_HD int nt16_int_of(int b4)
+{
+    return b4 == 1 ? 0 : b4 == 2 ? 1 : b4 == 4 ? 2 : b4 == 8 ? 3 : 4;
+}
+PLP_HD char up(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+PLP_HD char lo(char c) { return (c >= 'A' && c <= 'Z') ? (char)(c + 32) : c; }
+
+// reference character at relative column c as the reference prints it
+// ("(ref && pos < ref_len) ? ref[pos] : 'N'", bam_plcmd.c:667)
+PLP_HD char ref_char(const View &v, int64_t c)
+{
+    if (!v.ref || c >= v.ref_len_rel) return 'N';
+    int64_t i = c - v.ref_off;
+    if (i < 0 || i >= v.ref_n) return 'N';
+    return v.ref[i];
+}
+
+// per-column BED test: bed_overlap(bed, name, pos, pos+1) (bedidx.c:183-191).
+// The reference scans its sorted interval list from a linear-index hint; the
+// hint never skips an interval that contains pos, so the result is exactly
+// "some interval has beg <= pos < end".  The host passes the per-contig
+// intervals merged into a disjoint sorted union, which keeps that predicate.
+PLP_HD bool bed_pass(const View &v, int64_t c)
+{
+    if (!v.bed_active) return true;
+    const int64_t p = c + v.win_base;
+    int lo_ = 0, hi_ = v.n_bed;
+    while (lo_ < hi_) { int m = (lo_ + hi_) >> 1; if (v.bed_beg[m] <= p) lo_ = m + 1; else hi_ = m; }
+    return lo_ > 0 && v.bed_end[lo_ - 1] > p;
+}
+
+// ---- CIGAR -> column (stateless resolve_cigar2) -----------------------------
+// Finds the reference-consuming op that holds column c: its index k, first
+// column x and query offset y.  Short CIGARs are walked; long ones (long reads,
+// thousands of ops) use the per-op prefix arrays built by the read stage, so a
+// column costs O(log n_cigar) instead of O(n_cigar).
+constexpr int kCigarWalkMax = 8;
+PLP_HD void locate(const View &v, const ReadDesc &d, int32_t c, int &k, int32_t &x, int32_t &y, int &op, int &len)
+{
+    const uint32_t *cg = v.cigar + d.cig_off;
+    const int n = d.n_cigar;
+    if (n > kCigarWalkMax) {
+        const int32_t *cx = v.cig_x + d.cig_off;
+        int lo_ = 0, hi_ = n;
+        while (lo_ < hi_) { const int m = (lo_ + hi_) >> 1; if (cx[m] <= c) lo_ = m + 1; else hi_ = m; }
+        k = lo_ - 1; x = cx[k]; y = v.cig_y[d.cig_off + k];
+        op = cg[k] & 0xf; len = (int)(cg[k] >> 4);
+        return;
+    }
+    x = d.rpos; y = 0; op = 0; len = 0;
+    for (k = 0; k < n; ++k) {
+        op = cg[k] & 0xf; len = (int)(cg[k] >> 4);
+        if (is_refop(op)) {
+            if (c < x + len) break;
+            x += len;
+            if (is_mop(op)) y += len;
+        } else if (op == OP_I || op == OP_S) y += len;
+    }
+}
+
+PLP_HD void resolve(const View &v, const ReadDesc &d, int32_t c, Ent &e)
+{
+    e.is_head = (c == d.rpos);
+    e.is_tail = (c == d.rend - 1);
+    e.indel = 0; e.is_del = 0; e.is_refskip = 0;
+    if (d.fl & RD_SIMPLE) {  // [H][S] M [S][H]
+        e.qpos = d.qstart + (c - d.rpos);
+        e.k = -1;            // only needed for insertions, which a simple read has none of
+        return;
+    }
+    const uint32_t *cg = v.cigar + d.cig_off;
+    const int n = d.n_cigar;
+    int32_t x, y; int k, op, len;
+    locate(v, d, c, k, x, y, op, len);
+    e.k = k;
+    if (x + len - 1 == c && k + 1 < n) {  // last column of op k: look ahead
+        int op2 = cg[k + 1] & 0xf, l2 = (int)(cg[k + 1] >> 4);
+        if (op2 == OP_D && op != OP_D) {
+            e.indel = -l2;
+            for (int j = k + 2; j < n; ++j) { if ((cg[j] & 0xf) == OP_D) e.indel -= (int)(cg[j] >> 4); else break; }
+        } else if (op2 == OP_I) {
+            e.indel = l2;
+            for (int j = k + 2; j < n; ++j) {
+                int o = cg[j] & 0xf;
+                if (o == OP_I) e.indel += (int)(cg[j] >> 4);
+                else if (o != OP_P) break;
+            }
+        } else if (op2 == OP_P && k + 2 < n) {
+            int l3 = 0;
+            for (int j = k + 2; j < n; ++j) {
+                int o = cg[j] & 0xf;
+                if (o == OP_I) l3 += (int)(cg[j] >> 4);
+                else if (o == OP_D || o == OP_M || o == OP_N || o == OP_EQ || o == OP_X) break;
+            }
+            if (l3 > 0) e.indel = l3;
+        }
+    }
+    if (is_mop(op)) e.qpos = y + (c - x);
+    else { e.is_del = 1; e.qpos = y; e.is_refskip = (op == OP_N); }
+}
+
+// insertion after op k: number of printed symbols (pads + bases) and the
+// length of a deletion that follows directly (bam_plp_insertion_mod)
+PLP_HD int ins_scan(const ReadDesc &d, const uint32_t *cg, int k, int &del_len)
+{
+    int nb = 0;
+    del_len = 0;
+    for (int j = k + 1; j < d.n_cigar; ++j) {
+        int op = cg[j] & 0xf, l = (int)(cg[j] >> 4);
+        if (op == OP_P || op == OP_I) nb += l;
+        else { if (op == OP_D) del_len = l; break; }
+    }
+    return nb;
+}
+
+// base quality the reference tests against -Q ("qpos < l_qseq ? qual[qpos] : 0")
+PLP_HD int ent_qual(const View &v, const ReadDesc &d, const Ent &e)
+{
+    return e.qpos < d.l_qseq ? (int)v.qual[d.qoff + (uint64_t)e.qpos] : 0;
+}
+
+// ---- mpileup text for one (read, column) ------------------------------------
+PLP_HD int mp_entry_size(const MpConf &cf, const ReadDesc &d, const uint32_t *cg, const Ent &e)
+{
+    int sz = 1;
+    if (!cf.no_ends && e.is_head) sz += 2;
+    int del_len = -e.indel;
+    if (e.indel > 0) {
+        int len = ins_scan(d, cg, e.k, del_len);
+        if (cf.no_ins < 2) sz += 1 + ndigits((uint64_t)len);
+        if (!cf.no_ins) sz += len;
+    }
+    if (del_len > 0) {
+        if (cf.no_del < 2) sz += 1 + ndigits((uint64_t)del_len);
+        if (!cf.no_del) sz += del_len;
+    }
+    if (!cf.no_ends && e.is_tail) sz += 1;
+    return sz;
+}
+
+PLP_HD int mp_entry_write(const View &v, const MpConf &cf, const ReadDesc &d, const uint32_t *cg, const Ent &e,
+                          int32_t c, char *p)
+{
+    char *p0 = p;
+    const bool rev = d.fl & RD_REV;
+    if (!cf.no_ends && e.is_head) { *p++ = '^'; *p++ = (char)(d.mapq > 93 ? 126 : d.mapq + 33); }
+    if (!e.is_del) {
+        int ch = e.qpos < d.l_qseq ? base4(v.seq4, d.qoff, e.qpos) : 15;
+        if (v.ref) {
+            int rb = 15;
+            if ((int64_t)c < v.ref_len_rel) {
+                int64_t i = (int64_t)c - v.ref_off;
+                if (i >= 0 && i < v.ref_n) rb = nt16_of((unsigned char)v.ref[i]);
+            }
+            if (ch == rb) ch = 0;
+        }
+        *p++ = rev ? ",acmgrsvtwyhkdbn"[ch] : ".ACMGRSVTWYHKDBN"[ch];
+    } else *p++ = e.is_refskip ? (rev ? '<' : '>') : ((rev && cf.rev_del) ? '#' : '*');
+    int del_len = -e.indel;
+    if (e.indel > 0) {
+        int len = ins_scan(d, cg, e.k, del_len);
+        if (cf.no_ins < 2) { *p++ = '+'; p += put_u64(p, (uint64_t)len); }
+        if (!cf.no_ins) {
+            int j = 1;
+            for (int kk = e.k + 1; kk < d.n_cigar; ++kk) {
+                int op = cg[kk] & 0xf, l = (int)(cg[kk] >> 4);
+                if (op == OP_P) { for (int i = 0; i < l; ++i) *p++ = (rev && cf.rev_del) ? '#' : '*'; }
+                else if (op == OP_I) {
+                    for (int i = 0; i < l; ++i, ++j) {
+                        int q = e.qpos + j - (int)e.is_del;
+                        char b = q < d.l_qseq ? "=ACMGRSVTWYHKDBN"[base4(v.seq4, d.qoff, q)] : 'N';
+                        *p++ = rev ? lo(b) : up(b);
+                    }
+                } else break;
+            }
+        }
+    }
+    if (del_len > 0) {
+        if (cf.no_del < 2) { *p++ = '-'; p += put_u64(p, (uint64_t)del_len); }
+        if (!cf.no_del)
+            for (int j = 1; j <= del_len; ++j) {
+                // "(ref && (int)pos+j < ref_len) ? ref[pos+j] : 'N'" (bam_plcmd.c:158)
+                char b = ref_char(v, (int64_t)c + j);
+                *p++ = rev ? lo(b) : up(b);
+            }
+    }
+    if (!cf.no_ends && e.is_tail) *p++ = '$';
+    return (int)(p - p0);
+}
+
+// per (column, file) sizes
+struct MpFileSz {
+    int32_t nplp, cnt;
+    uint32_t seq_len, bp_len, bp5_len;
+};
+
+PLP_HD int32_t qpos5_of(const ReadDesc &d, const Ent &e)
+{
+    return (d.fl & RD_REV) ? d.l_qseq - e.qpos + (int)e.is_del : e.qpos + 1;
+}
+
+PLP_HD void mp_file_size(const View &v, const MpConf &cf, int f, int tile, int32_t c, MpFileSz &s)
+{
+    s.nplp = 0; s.cnt = 0; s.seq_len = 0; s.bp_len = 0; s.bp5_len = 0;
+    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
+    for (int32_t i = lo_; i < hi_; ++i) {
+        const ReadDesc d = v.desc[i];
+        if (c < d.rpos || c >= d.rend) continue;
+        const uint32_t *cg = v.cigar + d.cig_off;
+        Ent e;
+        resolve(v, d, c, e);
+        ++s.nplp;
+        if (ent_qual(v, d, e) < cf.min_baseQ) continue;
+        ++s.cnt;
+        s.seq_len += (uint32_t)mp_entry_size(cf, d, cg, e);
+        if (cf.out_qpos) s.bp_len += (uint32_t)ndigits((uint64_t)(e.qpos + 1)) + 1;
+        if (cf.out_qpos5) { int32_t q5 = qpos5_of(d, e); s.bp5_len += (uint32_t)(q5 < 0 ? 1 + ndigits((uint64_t)(-(int64_t)q5)) : ndigits((uint64_t)q5)) + 1; }
+    }
+}
+
+PLP_HD int mp_n_opt_cols(const MpConf &cf) { return (cf.out_mapq != 0) + (cf.out_qpos != 0) + (cf.out_qpos5 != 0) + cf.n_star_cols; }
+
+// bytes of the per-file section "\tcnt\tseq\tqual[\topt]*"
+PLP_HD uint32_t mp_file_section_len(const MpConf &cf, const MpFileSz &s)
+{
+    uint32_t n = 1 + (uint32_t)ndigits((uint64_t)s.cnt) + 1;
+    if (s.nplp == 0) return n + 3 + 2u * (uint32_t)mp_n_opt_cols(cf);
+    n += (s.seq_len ? s.seq_len : 1) + 1 + (s.cnt ? (uint32_t)s.cnt : 1);
+    if (cf.out_mapq) n += 1 + (s.cnt ? (uint32_t)s.cnt : 1);
+    if (cf.out_qpos) n += 1 + (s.cnt ? s.bp_len - 1 : 1);
+    if (cf.out_qpos5) n += 1 + (s.cnt ? s.bp5_len - 1 : 1);
+    n += 2u * (uint32_t)cf.n_star_cols;   // host-side columns are not produced here
+    return n;
+}
+
+PLP_HD int put_i32(char *p, int32_t v)
+{
+    if (v < 0) { *p = '-'; return 1 + put_u64(p + 1, (uint64_t)(-(int64_t)v)); }
+    return put_u64(p, (uint64_t)v);
+}
+
+// writes the per-file section; s must come from mp_file_size for the same column
+PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int32_t c, const MpFileSz &s, char *p)
+{
+    *p++ = '\t'; p += put_u64(p, (uint64_t)s.cnt); *p++ = '\t';
+    if (s.nplp == 0) {
+        *p++ = '*'; *p++ = '\t'; *p++ = '*';
+        for (int i = 0; i < mp_n_opt_cols(cf); ++i) { *p++ = '\t'; *p++ = '*'; }
+        return p;
+    }
+    char *ps = p;                                   // sequence column
+    char *pq = ps + (s.seq_len ? s.seq_len : 1) + 1; // quality column
+    char *pm = pq + (s.cnt ? s.cnt : 1);             // optional columns follow
+    char *pb = pm, *pb5;
+    if (cf.out_mapq) pb = pm + 1 + (s.cnt ? s.cnt : 1);
+    pb5 = pb;
+    if (cf.out_qpos) pb5 = pb + 1 + (s.cnt ? s.bp_len - 1 : 1);
+    char *pend = pb5;
+    if (cf.out_qpos5) pend = pb5 + 1 + (s.cnt ? s.bp5_len - 1 : 1);
+    if (!s.cnt) {
+        *ps = '*'; *pq = '*';
+        if (cf.out_mapq) { pm[0] = '\t'; pm[1] = '*'; }
+        if (cf.out_qpos) { pb[0] = '\t'; pb[1] = '*'; }
+        if (cf.out_qpos5) { pb5[0] = '\t'; pb5[1] = '*'; }
+    } else {
+        if (cf.out_mapq) *pm++ = '\t';
+        if (cf.out_qpos) *pb++ = '\t';
+        if (cf.out_qpos5) *pb5++ = '\t';
+        const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
+        int n = 0;
+        for (int32_t i = lo_; i < hi_; ++i) {
+            const ReadDesc d = v.desc[i];
+            if (c < d.rpos || c >= d.rend) continue;
+            const uint32_t *cg = v.cigar + d.cig_off;
+            Ent e;
+            resolve(v, d, c, e);
+            int q = ent_qual(v, d, e);
+            if (q < cf.min_baseQ) continue;
+            ps += mp_entry_write(v, cf, d, cg, e, c, ps);
+            *pq++ = (char)(q + 33 < 126 ? q + 33 : 126);
+            if (cf.out_mapq) { int m = d.mapq + 33; *pm++ = (char)(m > 126 ? 126 : m); }
+            if (cf.out_qpos) { if (n) *pb++ = ','; pb += put_i32(pb, e.qpos + 1); }
+            if (cf.out_qpos5) { if (n) *pb5++ = ','; pb5 += put_i32(pb5, qpos5_of(d, e)); }
+            ++n;
+        }
+    }
+    pq = p + (s.seq_len ? s.seq_len : 1);
+    *pq = '\t';
+    p = pend;
+    for (int i = 0; i < cf.n_star_cols; ++i) { *p++ = '\t'; *p++ = '*'; }
+    return p;
+}
+
+PLP_HD uint32_t mp_head_len(const View &v, int32_t c)
+{
+    return (uint32_t)v.name_len + 1 + (uint32_t)ndigits((uint64_t)(v.win_base + c + 1)) + 2;
+}
+PLP_HD char *mp_head_write(const View &v, int32_t c, char *p)
+{
+    for (int i = 0; i < v.name_len; ++i) *p++ = v.name[i];
+    *p++ = '\t';
+    p += put_u64(p, (uint64_t)(v.win_base + c + 1));
+    *p++ = '\t';
+    *p++ = ref_char(v, c);
+    return p;
+}
+
+// full line length for column c (0: the column is not reported)
+PLP_HD uint32_t mp_line_size(const View &v, const MpConf &cf, int tile, int32_t c, MpFileSz &s0)
+{
+    uint32_t body = 0;
+    bool any = false;
+    for (int f = 0; f < v.n_files; ++f) {
+        MpFileSz s;
+        mp_file_size(v, cf, f, tile, c, s);
+        if (f == 0) s0 = s;
+        any |= s.nplp > 0;
+        body += mp_file_section_len(cf, s);
+    }
+    if (!any && !(cf.all && c < v.ncols_all)) return 0;
+    if (!bed_pass(v, c)) return 0;
+    return mp_head_len(v, c) + body + 1;
+}
+
+PLP_HD void mp_line_write(const View &v, const MpConf &cf, int tile, int32_t c, const MpFileSz &s0, char *p)
+{
+    p = mp_head_write(v, c, p);
+    for (int f = 0; f < v.n_files; ++f) {
+        MpFileSz s;
+        if (f == 0) s = s0; else mp_file_size(v, cf, f, tile, c, s);
+        p = mp_file_write(v, cf, f, tile, c, s, p);
+    }
+    *p = '\n';
+}
+
+// ---- depth (bam2depth.c) ------------------------------------------------------
+// In depth mode ReadDesc.rend is bam_endpos (zero-length reads span one column).
+struct DpCol { int32_t depth; bool spanned; };
+
+PLP_HD void dp_file_column(const View &v, const DpConf &cf, int f, int tile, int32_t c, DpCol &o)
+{
+    o.depth = 0; o.spanned = false;
+    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
+    for (int32_t i = lo_; i < hi_; ++i) {
+        const ReadDesc d = v.desc[i];
+        if (c < d.rpos || c >= d.rend) continue;
+        o.spanned = true;
+        const int32_t clip = v.clip ? v.clip[i] : INT32_MIN;
+        if (d.fl & RD_SIMPLE) {
+            if (c < clip) continue;
+            int q = d.qstart + (c - d.rpos);
+            if (!cf.min_qual || v.qual[d.qoff + (uint64_t)q] >= cf.min_qual) ++o.depth;
+            continue;
+        }
+        int32_t x, y; int k, op, len;
+        locate(v, d, c, k, x, y, op, len);
+        if (k >= d.n_cigar || c < clip) continue;
+        if (is_mop(op)) {
+            int q = y + (c - x);
+            if (!cf.min_qual || v.qual[d.qoff + (uint64_t)q] >= cf.min_qual) ++o.depth;
+        } else if (op == OP_D && cf.count_del) {
+            // -J: a deletion column borrows the quality of the next query base (bam2depth.c:418-423)
+            if (y < d.l_qseq) { if (v.qual[d.qoff + (uint64_t)y] >= cf.min_qual) ++o.depth; }
+            else ++o.depth;
+        }
+    }
+}
+
+// ---- coverage (coverage.c:622-660) --------------------------------------------
+struct CvCol { uint32_t depth; uint32_t qbases; uint64_t sum_bq; uint32_t missing; bool count_base; };
+
+PLP_HD void cv_column(const View &v, int32_t min_baseQ, int tile, int32_t c, CvCol &o)
+{
+    o.depth = 0; o.qbases = 0; o.sum_bq = 0; o.missing = 0; o.count_base = false;
+    for (int f = 0; f < v.n_files; ++f) {
+        const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
+        int32_t dpos = 0;
+        for (int32_t i = lo_; i < hi_; ++i) {
+            const ReadDesc d = v.desc[i];
+            if (c < d.rpos || c >= d.rend) continue;
+            Ent e;
+            resolve(v, d, c, e);
+            ++dpos;
+            if (e.is_del || e.is_refskip) --dpos;
+            else if (e.qpos < d.l_qseq) {
+                int q = v.qual[d.qoff + (uint64_t)e.qpos];
+                if (q < min_baseQ) --dpos;
+                else { o.sum_bq += (uint64_t)q; ++o.qbases; }
+            } else ++o.missing;
+        }
+        if (dpos > 0) { o.count_base = true; o.depth += (uint32_t)dpos; }
+    }
+}
+
+}  // namespace plp

@@ -1,0 +1,187 @@
+"""Seeded synthetic workloads of SURVEY.md section 8(d), as SoA batches (and SAM text).
+
+One contig of `length` bp at `depth`x with `read_len` bp paired reads:
+  reference  uniform ACGT, 0.1 % of positions inside short N runs
+  pairs      insert size ~ N(400, 50), proper-pair flags 99/147 (and 83/163),
+             so ~15 % of pairs overlap; both mates on this contig
+  mapq       60 for 90 % of reads, uniform 0..59 otherwise
+  qualities  Illumina-like: Q37 plateau decaying towards Q20 at the 3' end, +-3 noise, floor 2
+  bases      reference with substitutions at the per-base error rate (+0.1 % SNPs)
+  CIGAR      97 % <L>M, 1.5 % one insertion (<=10), 1.5 % one deletion (<=10),
+             2 % soft-clipped end, 0.1 % ref-skip (N)  (fractions configurable)
+  flags      0.5 % get DUP / SECONDARY / QCFAIL to exercise the filters
+Everything derives from numpy Generator(seed); the same seed gives the same
+batch on every machine.  `write_sam()` writes the identical records as SAM text
+so the CPU oracle (or a real samtools) reads the same data.
+"""
+import numpy as np
+
+NT16 = {'A': 1, 'C': 2, 'G': 4, 'T': 8, 'N': 15}
+_CODE2CH = np.frombuffer(b'=ACMGRSVTWYHKDBN', dtype=np.uint8)
+
+
+def make_reference(length, seed=1, n_frac=0.001):
+    rng = np.random.default_rng(seed)
+    ref = np.frombuffer(b'ACGT', dtype=np.uint8)[rng.integers(0, 4, size=length)]
+    n_runs = max(1, int(length * n_frac / 20)) if n_frac > 0 else 0
+    for s in rng.integers(0, max(1, length - 20), size=n_runs):
+        ref[s:s + int(rng.integers(5, 35))] = ord('N')
+    return ref
+
+
+def _name_odd(pair_id, width=9):
+    """__ac_Wang_hash(__ac_X31_hash_string("p%0*d")) & 1, vectorised (uint32 wraparound)."""
+    h = np.full(pair_id.shape, ord('p'), dtype=np.uint32)
+    div = 10 ** (width - 1)
+    with np.errstate(over='ignore'):
+        for _ in range(width):
+            d = ((pair_id // div) % 10).astype(np.uint32) + np.uint32(ord('0'))
+            h = h * np.uint32(31) + d
+            div //= 10
+        h = h + ~(h << np.uint32(15)); h ^= (h >> np.uint32(10)); h = h + (h << np.uint32(3)); h ^= (h >> np.uint32(6))
+        h = h + ~(h << np.uint32(11)); h ^= (h >> np.uint32(16))
+    return (h & 1).astype(np.uint8)
+
+
+def make_batch(length=1_000_000, depth=30, read_len=150, seed=2, ref=None, ref_seed=1, with_ref=True, tid=0,
+               tid_name='chr1', frac_ins=0.015, frac_del=0.015, frac_clip=0.02, frac_skip=0.001, frac_flag=0.005,
+               paired=True):
+    """Returns a dict with the b200_batch_t arrays (+ 'pair_id', 'ref' ...)."""
+    rng = np.random.default_rng(seed)
+    L = read_len
+    if ref is None:
+        ref = make_reference(length, ref_seed)
+    n_pairs = int(round(depth * length / (2.0 * L)))
+    isize = np.clip(rng.normal(400, 50, n_pairs).round().astype(np.int64), L, 1000)
+    start = rng.integers(0, max(1, length - 1100), size=n_pairs).astype(np.int64)
+    # which mate is first / forward
+    fwd_first = rng.random(n_pairs) < 0.5
+    n = 2 * n_pairs
+    pair_id = np.repeat(np.arange(n_pairs, dtype=np.int64), 2)
+    is_second = np.tile(np.array([0, 1], dtype=np.int8), n_pairs)          # 0: leftmost mate, 1: rightmost
+    pos = np.where(is_second == 0, np.repeat(start, 2), np.repeat(start + isize - L, 2))
+    rev = is_second.astype(bool)                                           # rightmost mate is the reverse one
+    read1 = np.where(np.repeat(fwd_first, 2), is_second == 0, is_second == 1)
+    flag = np.full(n, 1 | 2, dtype=np.uint16)
+    flag |= np.where(rev, 16, 32).astype(np.uint16)
+    flag |= np.where(read1, 64, 128).astype(np.uint16)
+    if not paired:
+        flag = np.where(rev, 16, 0).astype(np.uint16)
+    # CIGAR class: 0 M, 1 ins, 2 del, 3 clip-left, 4 clip-right, 5 ref-skip
+    u = rng.random(n)
+    cls = np.zeros(n, dtype=np.int8)
+    edges = np.cumsum([frac_ins, frac_del, frac_clip / 2, frac_clip / 2, frac_skip])
+    cls[u < edges[4]] = 5; cls[u < edges[3]] = 4; cls[u < edges[2]] = 3; cls[u < edges[1]] = 2; cls[u < edges[0]] = 1
+    k = np.minimum(rng.geometric(0.4, n), 10).astype(np.int64)              # indel / clip length
+    k = np.where(cls == 5, rng.integers(200, 2000, n), k)
+    k = np.where((cls == 3) | (cls == 4), rng.integers(1, 30, n), k)
+    a = rng.integers(10, L - 20, n).astype(np.int64)                       # bases before the event
+    # query index -> reference index (or -1 = random base)
+    j = np.arange(L, dtype=np.int64)[None, :]
+    A, K, P, CL = a[:, None], k[:, None], pos[:, None], cls[:, None]
+    refidx = P + j
+    refidx = np.where((CL == 1) & (j >= A) & (j < A + K), -1, refidx)
+    refidx = np.where((CL == 1) & (j >= A + K), P + j - K, refidx)
+    refidx = np.where(((CL == 2) | (CL == 5)) & (j >= A), P + j + K, refidx)
+    refidx = np.where((CL == 3) & (j < K), -1, refidx)
+    refidx = np.where((CL == 3) & (j >= K), P + j - K, refidx)
+    refidx = np.where((CL == 4) & (j >= L - K), -1, refidx)
+    # qualities
+    prof = np.where(np.arange(L) < L * 0.6, 37.0, 37.0 - 17.0 * (np.arange(L) - L * 0.6) / (L * 0.4))
+    q = np.clip(np.round(prof[None, :] + rng.normal(0, 3, (n, L))), 2, 41).astype(np.uint8)
+    q = np.where(rev[:, None], q[:, ::-1], q)                              # 3' end is the left end of a reverse read
+    # bases
+    safe = np.clip(refidx, 0, length - 1)
+    base = ref[safe]
+    rnd = np.frombuffer(b'ACGT', dtype=np.uint8)[rng.integers(0, 4, size=(n, L))]
+    perr = 10.0 ** (-q.astype(np.float64) / 10.0) + 0.001
+    mut = rng.random((n, L)) < perr
+    base = np.where((refidx < 0) | mut | (refidx >= length), rnd, base)
+    lut = np.full(256, 15, dtype=np.uint8)
+    for ch, v in NT16.items():
+        lut[ord(ch)] = v
+    code = lut[base]
+    # mapq + flags
+    mapq = np.where(rng.random(n) < 0.9, 60, rng.integers(0, 60, n)).astype(np.uint8)
+    ff = rng.random(n)
+    flag = flag | np.where(ff < frac_flag / 3, 1024, 0).astype(np.uint16)
+    flag = flag | np.where((ff >= frac_flag / 3) & (ff < 2 * frac_flag / 3), 256, 0).astype(np.uint16)
+    flag = flag | np.where((ff >= 2 * frac_flag / 3) & (ff < frac_flag), 512, 0).astype(np.uint16)
+    # sort by position (stable: keeps pair order for ties)
+    order = np.argsort(pos, kind='stable')
+    pos, flag, mapq, cls, k, a, pair_id, code, q = pos[order], flag[order], mapq[order], cls[order], k[order], a[order], pair_id[order], code[order], q[order]
+    # CIGAR ops
+    n_cigar = np.where(cls == 0, 1, np.where((cls == 3) | (cls == 4), 2, 3)).astype(np.uint32)
+    cigar_off = np.concatenate([[0], np.cumsum(n_cigar)[:-1]]).astype(np.uint64)
+    cigar = np.zeros(int(n_cigar.sum()), dtype=np.uint32)
+    M, I, D, N_, S = 0, 1, 2, 3, 4
+    o = cigar_off.astype(np.int64)
+    m0 = cls == 0; cigar[o[m0]] = (L << 4) | M
+    for c_, op in ((1, I), (2, D), (5, N_)):
+        m = cls == c_
+        cigar[o[m]] = (a[m].astype(np.uint32) << 4) | M
+        cigar[o[m] + 1] = (k[m].astype(np.uint32) << 4) | op
+        rest = (L - a[m] - (k[m] if c_ == 1 else 0)).astype(np.uint32)
+        cigar[o[m] + 2] = (rest << 4) | M
+    m = cls == 3; cigar[o[m]] = (k[m].astype(np.uint32) << 4) | S; cigar[o[m] + 1] = ((L - k[m]).astype(np.uint32) << 4) | M
+    m = cls == 4; cigar[o[m]] = ((L - k[m]).astype(np.uint32) << 4) | M; cigar[o[m] + 1] = (k[m].astype(np.uint32) << 4) | S
+    rlen = np.where(cls == 1, L - k, np.where((cls == 2) | (cls == 5), L + k, np.where((cls == 3) | (cls == 4), L - k, L))).astype(np.int64)
+    # mates
+    by_pair = np.argsort(pair_id, kind='stable')
+    first, second = by_pair[0::2], by_pair[1::2]
+    prev = np.full(n, -1, dtype=np.int64)
+    prev[second] = first
+    mpos = np.zeros(n, dtype=np.int64); mpos[first] = pos[second]; mpos[second] = pos[first]
+    tl = np.zeros(n, dtype=np.int64)
+    span = np.maximum(pos[second] + rlen[second], pos[first] + rlen[first]) - pos[first]
+    tl[first] = span; tl[second] = -span
+    if not paired:
+        prev[:] = -1; mpos[:] = -1; tl[:] = 0
+    # pack
+    lq = L + (L & 1)
+    qual = np.zeros((n, lq), dtype=np.uint8); qual[:, :L] = q
+    cpad = np.zeros((n, lq), dtype=np.uint8); cpad[:, :L] = code
+    seq4 = ((cpad[:, 0::2] << 4) | cpad[:, 1::2]).reshape(-1)
+    qual_off = (np.arange(n, dtype=np.uint64) * np.uint64(lq))
+    rbits = (_name_odd(pair_id) * 2).astype(np.uint8)
+    return dict(file_start=np.array([0, n], dtype=np.int64), pos=pos.astype(np.int64), flag=flag, mapq=mapq,
+                l_qseq=np.full(n, L, dtype=np.int32), n_cigar=n_cigar, cigar_off=cigar_off, qual_off=qual_off,
+                mtid=np.full(n, tid if paired else -1, dtype=np.int32), mpos=mpos, isize=tl, prev_same_name=prev, rbits=rbits,
+                cigar=cigar, seq4=np.ascontiguousarray(seq4), qual=np.ascontiguousarray(qual.reshape(-1)),
+                tid=tid, tid_len=length, tid_name=tid_name, ref=ref if with_ref else None, ref_beg=0, ref_len=length,
+                pair_id=pair_id, read_len=L, ref_full=ref)
+
+
+def algorithmic_bytes_in(soa, overlap=True):
+    """sum over reads of ceil(l/2) + l + 4*n_cigar + 24 (+24 mate fields) (+ ref bytes touched)."""
+    l = soa['l_qseq'].astype(np.int64)
+    b = int(((l + 1) // 2 + l + 4 * soa['n_cigar'].astype(np.int64) + 24 + (24 if overlap else 0)).sum())
+    return b
+
+
+def write_fasta(path, name, ref, width=60):
+    with open(path, 'w') as f:
+        f.write(f'>{name}\n')
+        s = ref.tobytes().decode()
+        for i in range(0, len(s), width):
+            f.write(s[i:i + width] + '\n')
+
+
+def write_sam(path, soa, max_reads=None):
+    """The same records as SAM text (names p%09d, so the name-hash bit matches rbits)."""
+    name = soa['tid_name']; L = soa['read_len']
+    lq = L + (L & 1)
+    n = len(soa['pos']) if max_reads is None else min(max_reads, len(soa['pos']))
+    seq4 = soa['seq4'].reshape(-1, lq // 2); qual = soa['qual'].reshape(-1, lq)
+    ops = 'MIDNSHP=XB'
+    with open(path, 'w') as f:
+        f.write(f'@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:{name}\tLN:{soa["tid_len"]}\n')
+        for i in range(n):
+            co = int(soa['cigar_off'][i]); nc = int(soa['n_cigar'][i])
+            cg = ''.join(f'{int(c) >> 4}{ops[int(c) & 15]}' for c in soa['cigar'][co:co + nc])
+            nib = np.empty(lq, dtype=np.uint8); nib[0::2] = seq4[i] >> 4; nib[1::2] = seq4[i] & 15
+            seq = _CODE2CH[nib[:L]].tobytes().decode()
+            ql = (qual[i, :L] + 33).tobytes().decode()
+            paired = bool(soa['flag'][i] & 1)
+            f.write(f'p{int(soa["pair_id"][i]):09d}\t{int(soa["flag"][i])}\t{name}\t{int(soa["pos"][i]) + 1}\t{int(soa["mapq"][i])}\t{cg}\t'
+                    f'{"=" if paired else "*"}\t{int(soa["mpos"][i]) + 1}\t{int(soa["isize"][i])}\t{seq}\t{ql}\n')

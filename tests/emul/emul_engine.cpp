@@ -1,0 +1,223 @@
+// emul_engine.cpp -- DEBUG HARNESS, NOT PART OF THE PRODUCT.
+//
+// Implements the C ABI of include/b200_pileup.h by stepping the very same
+// __host__ __device__ per-read / per-column functions the CUDA kernels call
+// (samtools_b200/csrc/plp_core.h, plp_stage.h) in a plain single-threaded
+// loop.  It exists so that the column arithmetic and the host drivers can be
+// debugged in the dev container, which has no GPU.  It is built only by
+// tests/emul/build.sh, is never linked into libb200pileup.so or b200samtools,
+// is never used as a fallback, and is not a measured or shipped path.
+// BAQ (warp-cooperative kernel) and GL are NOT emulated: calls needing them fail.
+#include "../../include/b200_pileup.h"
+#include "../../samtools_b200/csrc/plp_core.h"
+#include "../../samtools_b200/csrc/plp_stage.h"
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <queue>
+#include <string>
+#include <vector>
+
+using namespace plp;
+
+struct b200_engine {
+    std::string err, name;
+    b200_batch_t b; b200_stage_conf_t cf;
+    std::vector<uint8_t> qual, mapq, state; std::vector<int32_t> rlen, endv, pmax, glo, ghi, clip, cig_x, cig_y; std::vector<ReadDesc> desc;
+    std::vector<int64_t> next, bedb, bede;
+    std::string ref;
+    StageAcc acc;
+    int64_t win_base = 0, ncols_cov = 0, ncols_all = 0; int32_t ncols_max = 0, n_groups = 0;
+    bool staged = false, has_clip = false;
+};
+
+extern "C" {
+const char *b200_version(void) { return "emulation harness (debug only)"; }
+const char *b200_last_error(const b200_engine_t *e) { return e->err.c_str(); }
+double b200_last_kernel_ms(const b200_engine_t *) { return 0; }
+double b200_last_stage_ms(const b200_engine_t *) { return 0; }
+int64_t b200_launch_count(const b200_engine_t *) { return 0; }
+int b200_engine_create(int, b200_engine_t **out) { *out = new b200_engine(); return 0; }
+void b200_engine_destroy(b200_engine_t *e) { delete e; }
+
+static RawSoA raw(b200_engine *e)
+{
+    const b200_batch_t &b = e->b;
+    RawSoA r;
+    r.pos = b.pos; r.flag = b.flag; r.mapq = e->mapq.data(); r.l_qseq = b.l_qseq; r.n_cigar = b.n_cigar; r.cigar_off = b.cigar_off;
+    r.qual_off = b.qual_off; r.mtid = b.mtid; r.mpos = b.mpos; r.isize = b.isize; r.prev = b.prev_same_name; r.rbits = b.rbits;
+    r.cigar = b.cigar; r.seq4 = b.seq4; r.qual = e->qual.data();
+    r.ref = b.ref && b.ref_len > 0 ? e->ref.data() : nullptr; r.ref_beg = b.ref_beg; r.ref_n = b.ref_n; r.ref_len = r.ref ? b.ref_len : 0;
+    r.n = b.n_reads; r.tid = b.tid;
+    return r;
+}
+
+static void build_ranges(b200_engine *e, int *max_range)
+{
+    const b200_batch_t &b = e->b;
+    const int64_t n = b.n_reads;
+    e->pmax.assign((size_t)n + 1, INT32_MIN);
+    for (int f = 0; f < b.n_files; ++f) {
+        int32_t m = INT32_MIN;
+        for (int64_t i = b.file_start[f]; i < b.file_start[f + 1]; ++i) { m = std::max(m, e->endv[(size_t)i]); e->pmax[(size_t)i] = m; }
+    }
+    e->glo.assign((size_t)e->n_groups * b.n_files + 1, 0); e->ghi = e->glo;
+    *max_range = 0;
+    for (int f = 0; f < b.n_files; ++f)
+        for (int g = 0; g < e->n_groups; ++g) {
+            const int64_t fs = b.file_start[f], fe = b.file_start[f + 1];
+            const int32_t c0 = g * 32, c1 = c0 + 31;
+            int64_t lo = fs, hi = fe;
+            while (lo < hi) { int64_t m = (lo + hi) >> 1; if (e->pmax[(size_t)m] > c0) hi = m; else lo = m + 1; }
+            const int64_t first = lo;
+            hi = fe;
+            while (lo < hi) { int64_t m = (lo + hi) >> 1; if (e->desc[(size_t)m].rpos > c1) hi = m; else lo = m + 1; }
+            const int64_t last = std::max(lo, first);
+            e->glo[(size_t)f * e->n_groups + g] = (int32_t)first; e->ghi[(size_t)f * e->n_groups + g] = (int32_t)last;
+            *max_range = std::max(*max_range, (int)(last - first));
+        }
+}
+
+int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t *cf, b200_stage_stats_t *stats)
+{
+    e->b = *b; e->cf = *cf; e->name = b->tid_name ? b->tid_name : "";
+    const int64_t n = b->n_reads;
+    e->qual.assign(b->qual, b->qual + b->qual_bytes); e->qual.resize(b->qual_bytes + 8, 0);
+    e->mapq.assign(b->mapq, b->mapq + n); e->mapq.resize((size_t)n + 1);
+    e->ref.assign(b->ref ? b->ref : "", b->ref ? (size_t)b->ref_n : 0);
+    e->state.assign((size_t)n + 1, 0); e->rlen.assign((size_t)n + 1, 0); e->desc.assign((size_t)n + 1, ReadDesc());
+    e->endv.assign((size_t)n + 1, INT32_MIN);
+    e->cig_x.assign((size_t)b->n_cigar_total + 1, 0); e->cig_y.assign((size_t)b->n_cigar_total + 1, 0);
+    memset(&e->acc, 0, sizeof e->acc); e->acc.max_rend = INT32_MIN;
+    e->win_base = cf->beg > 0 ? cf->beg : 0;
+    RawSoA r = raw(e);
+    for (int64_t i = 0; i < n; ++i) stage_prep1(r, *cf, i, e->state.data(), e->rlen.data(), &e->acc);
+    if (cf->mode == B200_MODE_MPILEUP && cf->baq && r.ref) {
+        for (int64_t i = 0; i < n; ++i)
+            if (e->state[(size_t)i] == ST_ALIVE && !(b->rbits && (b->rbits[i] & B200_RB_BAQ_DONE)) && b->l_qseq[i] > 0 && e->qual[b->qual_off[i]] != 0xff) {
+                e->err = "emulation harness: the BAQ kernel is not emulated"; return -1;
+            }
+    }
+    for (int64_t i = 0; i < n; ++i) stage_prep2(r, *cf, i, e->state.data());
+    for (int64_t i = 0; i < n; ++i) stage_build_desc(r, *cf, i, e->state.data(), e->rlen.data(), e->desc.data(), e->endv.data(), &e->acc, e->win_base, e->cig_x.data(), e->cig_y.data());
+    const int32_t max_rend = e->acc.n_kept ? e->acc.max_rend : 0;
+    int64_t wend = cf->end - e->win_base, cov = max_rend > 0 ? max_rend : 0;
+    if (cov > wend) cov = wend;
+    int64_t allc = std::min<int64_t>(cf->end, b->tid_len) - e->win_base; if (allc < 0) allc = 0;
+    e->ncols_cov = cov; e->ncols_all = allc; e->ncols_max = (int32_t)std::max(cov, allc);
+    e->n_groups = (e->ncols_max + 31) / 32 + 1;
+    int max_range = 0;
+    build_ranges(e, &max_range);
+    if (cf->mode != B200_MODE_DEPTH && cf->max_depth > 0 && 2LL * max_range + 1 > (int64_t)cf->max_depth) {
+        bool changed = false;
+        for (int f = 0; f < b->n_files; ++f) {
+            std::priority_queue<int32_t, std::vector<int32_t>, std::greater<int32_t>> ends;
+            bool have = false; int32_t pp = 0;
+            for (int64_t i = b->file_start[f]; i < b->file_start[f + 1]; ++i) {
+                if (e->state[(size_t)i] != ST_KEEP) continue;
+                const int32_t pos = e->desc[(size_t)i].rpos, end = pos + e->rlen[(size_t)i];
+                if (have) {
+                    while (!ends.empty() && ends.top() < pp) ends.pop();
+                    if (pos == pp && (int64_t)ends.size() + 1 > (int64_t)cf->max_depth) { e->state[(size_t)i] = ST_MAXDROP; changed = true; continue; }
+                }
+                ends.push(end); have = true; pp = pos;
+            }
+        }
+        if (changed) {
+            for (int64_t i = 0; i < n; ++i) if (e->state[(size_t)i] == ST_MAXDROP) { e->desc[(size_t)i].rend = e->desc[(size_t)i].rpos; e->endv[(size_t)i] = INT32_MIN; }
+            build_ranges(e, &max_range);
+        }
+    }
+    e->has_clip = false;
+    if (b->prev_same_name && ((cf->mode == B200_MODE_MPILEUP && cf->overlaps) || (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps))) {
+        e->next.assign((size_t)n + 1, -1);
+        for (int64_t i = 0; i < n; ++i) if (b->prev_same_name[i] >= 0) e->next[(size_t)b->prev_same_name[i]] = i;
+        if (cf->mode == B200_MODE_MPILEUP) {
+            for (int64_t i = 0; i < n; ++i) overlap_chain(r, i, e->next.data(), e->state.data(), e->rlen.data(), b->file_start, b->n_files);
+        } else {
+            e->clip.assign((size_t)n + 1, INT32_MIN);
+            for (int64_t i = 0; i < n; ++i) depth_clip_chain(r, i, e->next.data(), e->state.data(), e->rlen.data(), e->clip.data(), e->win_base);
+            e->has_clip = true;
+        }
+    }
+    e->staged = true;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_kept = (int64_t)e->acc.n_kept; stats->n_kept_in_window = (int64_t)e->acc.n_kept_in_window;
+        stats->n_reads = e->acc.n_reads; stats->n_selected_reads = e->acc.n_selected; stats->summed_mapq = e->acc.summed_mapq;
+        stats->out_bound = 0; stats->n_cols = e->ncols_max;
+    }
+    return 0;
+}
+
+static void fill_view(b200_engine *e, View &v, const int64_t *bb, const int64_t *be, int nb, int active, int all)
+{
+    const b200_batch_t &b = e->b;
+    v.desc = e->desc.data(); v.cigar = b.cigar; v.cig_x = e->cig_x.data(); v.cig_y = e->cig_y.data(); v.seq4 = b.seq4; v.qual = e->qual.data();
+    v.clip = e->has_clip ? e->clip.data() : nullptr;
+    v.ref = (b.ref && b.ref_len > 0) ? e->ref.data() : nullptr;
+    v.ref_off = b.ref_beg - e->win_base; v.ref_n = b.ref_n; v.ref_len_rel = (v.ref ? b.ref_len : 0) - e->win_base;
+    v.n_files = b.n_files; v.file_start = b.file_start; v.tile_lo = e->glo.data(); v.tile_hi = e->ghi.data();
+    v.n_tiles = e->n_groups; v.tile_cols = 32; v.win_base = e->win_base;
+    v.ncols_all = all ? (int32_t)e->ncols_all : 0;
+    v.ncols = (int32_t)(all ? std::max(e->ncols_cov, e->ncols_all) : e->ncols_cov);
+    v.name = e->name.c_str(); v.name_len = (int32_t)e->name.size();
+    v.bed_beg = bb; v.bed_end = be; v.n_bed = nb; v.bed_active = active;
+}
+
+static int emit(b200_engine *e, const std::string &s, char *out, size_t cap, size_t *out_len)
+{
+    *out_len = s.size();
+    if (out) { if (s.size() > cap) { e->err = "output buffer too small"; return -2; } memcpy(out, s.data(), s.size()); }
+    return 0;
+}
+
+int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out, size_t cap, size_t *out_len)
+{
+    View v; fill_view(e, v, c->bed_beg, c->bed_end, c->n_bed, c->bed_active, c->all);
+    MpConf cf{c->min_baseQ, c->all, c->rev_del, c->no_ins, c->no_del, c->no_ends, c->out_mapq, c->out_qpos, c->out_qpos5, c->n_star_cols};
+    std::string s;
+    for (int32_t col = 0; col < v.ncols; ++col) {
+        MpFileSz s0;
+        uint32_t len = mp_line_size(v, cf, col >> 5, col, s0);
+        if (!len) continue;
+        size_t at = s.size(); s.resize(at + len, '?');
+        mp_line_write(v, cf, col >> 5, col, s0, &s[at]);
+    }
+    return emit(e, s, out, cap, out_len);
+}
+
+int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, char *out, size_t cap, size_t *out_len)
+{
+    View v; fill_view(e, v, c->bed_beg, c->bed_end, c->n_bed, c->bed_active, c->all);
+    DpConf cf{c->min_qual, c->count_del, c->all};
+    std::string s;
+    for (int32_t col = 0; col < v.ncols; ++col) {
+        bool any = false; std::vector<int32_t> d((size_t)v.n_files);
+        for (int f = 0; f < v.n_files; ++f) { DpCol o; dp_file_column(v, cf, f, col >> 5, col, o); d[(size_t)f] = o.depth; any |= o.spanned; }
+        if (!any && !(cf.all && col < v.ncols_all)) continue;
+        if (!bed_pass(v, col)) continue;
+        s += e->name; s += '\t'; s += std::to_string(v.win_base + col + 1);
+        for (int f = 0; f < v.n_files; ++f) { s += '\t'; s += std::to_string(d[(size_t)f]); }
+        s += '\n';
+    }
+    return emit(e, s, out, cap, out_len);
+}
+
+int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b200_coverage_sums_t *sums)
+{
+    View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);
+    memset(sums, 0, sizeof *sums);
+    for (int32_t col = 0; col < v.ncols; ++col) {
+        CvCol o; cv_column(v, c->min_baseQ, col >> 5, col, o);
+        sums->missing_qual += o.missing;
+        if (o.count_base && o.depth >= (uint32_t)c->min_depth) { sums->n_covered_bases++; sums->summed_coverage += o.depth; sums->summed_baseQ += o.sum_bq; sums->quality_bases += o.qbases; }
+    }
+    return 0;
+}
+int b200_glf(b200_engine_t *e, int32_t, int64_t *, int64_t *, int32_t *, float *, float *, size_t) { e->err = "emulation harness: GL not emulated"; return -1; }
+int b200_fetch_qual(b200_engine_t *e, uint8_t *q, size_t cap) { memcpy(q, e->qual.data(), std::min(cap, e->qual.size())); return 0; }
+int b200_fetch_mapq_keep(b200_engine_t *e, uint8_t *m, uint8_t *k, size_t n) { n = std::min(n, (size_t)e->b.n_reads); if (m) memcpy(m, e->mapq.data(), n); if (k) memcpy(k, e->state.data(), n); return 0; }
+int b200_pileup_entries(b200_engine_t *e, int32_t, int64_t, int64_t, uint32_t *, b200_pileup1_t *, size_t, size_t *) { e->err = "emulation harness: entries not emulated"; return -1; }
+}
