@@ -1,0 +1,42 @@
+"""Region sharding across GPUs.
+
+The pileup path shards by genome region with no data-path exchange: shard s
+owns columns [beg_s, end_s) and stages every read overlapping them (the same
+rule as `-r`).  The only collective is the gather of per-shard column
+summaries (bytes emitted, columns, reads) to every rank / rank 0, which is what
+the emitter needs to concatenate shard outputs in genome order.
+Works over NCCL (CUDA tensors) and gloo (CPU tensors; used by the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def plan_shards(length, world, align=4096):
+    """Equal-width contiguous shards [beg,end) of a contig, aligned to `align` columns."""
+    per = -(-length // world)
+    per = -(-per // align) * align
+    return [(min(r * per, length), min((r + 1) * per, length)) for r in range(world)]
+
+
+def gather_summaries(local, device='cpu'):
+    """local: sequence of ints (e.g. [bytes_out, n_cols, n_reads]).  Returns a
+    (world, len(local)) int64 tensor on every rank (all_gather) plus the
+    exclusive prefix of column 0 (this rank's byte offset in the concatenated output)."""
+    t = torch.tensor(list(local), dtype=torch.int64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        allv = torch.stack(out)
+        rank = dist.get_rank()
+    else:
+        allv = t[None, :]
+        rank = 0
+    offset = int(allv[:rank, 0].sum().item())
+    return allv, offset
+
+
+def max_over_ranks(x, device='cpu'):
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -53,7 +53,7 @@ def make_batch(length=1_000_000, depth=30, read_len=150, seed=2, ref=None, ref_s
         ref = make_reference(length, ref_seed)
     n_pairs = int(round(depth * length / (2.0 * L)))
     isize = np.clip(rng.normal(400, 50, n_pairs).round().astype(np.int64), L, 1000)
-    start = rng.integers(0, max(1, length - 1100), size=n_pairs).astype(np.int64)
+    start = rng.integers(0, max(1, length - 3200), size=n_pairs).astype(np.int64)   # reads (even with a 2 kb N skip) stay inside the contig
     # which mate is first / forward
     fwd_first = rng.random(n_pairs) < 0.5
     n = 2 * n_pairs
@@ -76,27 +76,31 @@ def make_batch(length=1_000_000, depth=30, read_len=150, seed=2, ref=None, ref_s
     k = np.where(cls == 5, rng.integers(200, 2000, n), k)
     k = np.where((cls == 3) | (cls == 4), rng.integers(1, 30, n), k)
     a = rng.integers(10, L - 20, n).astype(np.int64)                       # bases before the event
-    # query index -> reference index (or -1 = random base)
-    j = np.arange(L, dtype=np.int64)[None, :]
-    A, K, P, CL = a[:, None], k[:, None], pos[:, None], cls[:, None]
-    refidx = P + j
-    refidx = np.where((CL == 1) & (j >= A) & (j < A + K), -1, refidx)
-    refidx = np.where((CL == 1) & (j >= A + K), P + j - K, refidx)
-    refidx = np.where(((CL == 2) | (CL == 5)) & (j >= A), P + j + K, refidx)
-    refidx = np.where((CL == 3) & (j < K), -1, refidx)
-    refidx = np.where((CL == 3) & (j >= K), P + j - K, refidx)
-    refidx = np.where((CL == 4) & (j >= L - K), -1, refidx)
+    # query index -> reference index (or -1 = random base); only the ~6 % non-<L>M reads need fixing up
+    j = np.arange(L, dtype=np.int32)[None, :]
+    refidx = pos.astype(np.int32)[:, None] + j
+    sp = np.nonzero(cls != 0)[0]
+    if len(sp):
+        A, K, P, CL = a[sp, None].astype(np.int32), k[sp, None].astype(np.int32), pos[sp, None].astype(np.int32), cls[sp, None]
+        r = P + j
+        r = np.where((CL == 1) & (j >= A) & (j < A + K), -1, r)
+        r = np.where((CL == 1) & (j >= A + K), P + j - K, r)
+        r = np.where(((CL == 2) | (CL == 5)) & (j >= A), P + j + K, r)
+        r = np.where((CL == 3) & (j < K), -1, r)
+        r = np.where((CL == 3) & (j >= K), P + j - K, r)
+        r = np.where((CL == 4) & (j >= L - K), -1, r)
+        refidx[sp] = r
     # qualities
-    prof = np.where(np.arange(L) < L * 0.6, 37.0, 37.0 - 17.0 * (np.arange(L) - L * 0.6) / (L * 0.4))
-    q = np.clip(np.round(prof[None, :] + rng.normal(0, 3, (n, L))), 2, 41).astype(np.uint8)
-    q = np.where(rev[:, None], q[:, ::-1], q)                              # 3' end is the left end of a reverse read
+    prof = np.where(np.arange(L) < L * 0.6, 37.0, 37.0 - 17.0 * (np.arange(L) - L * 0.6) / (L * 0.4)).astype(np.float32)
+    q = np.clip(np.rint(prof[None, :] + 3.0 * rng.standard_normal((n, L), dtype=np.float32)), 2, 41).astype(np.uint8)
+    q[rev] = q[rev, ::-1]                                                  # 3' end is the left end of a reverse read
     # bases
-    safe = np.clip(refidx, 0, length - 1)
-    base = ref[safe]
-    rnd = np.frombuffer(b'ACGT', dtype=np.uint8)[rng.integers(0, 4, size=(n, L))]
-    perr = 10.0 ** (-q.astype(np.float64) / 10.0) + 0.001
-    mut = rng.random((n, L)) < perr
-    base = np.where((refidx < 0) | mut | (refidx >= length), rnd, base)
+    base = ref[np.clip(refidx, 0, length - 1)]
+    perr = (10.0 ** (-np.arange(64, dtype=np.float32) / 10.0) + 0.001).astype(np.float32)[q]
+    mut = rng.random((n, L), dtype=np.float32) < perr
+    mut |= (refidx < 0) | (refidx >= length)
+    nm = int(mut.sum())
+    base[mut] = np.frombuffer(b'ACGT', dtype=np.uint8)[rng.integers(0, 4, size=nm, dtype=np.uint8)]
     lut = np.full(256, 15, dtype=np.uint8)
     for ch, v in NT16.items():
         lut[ord(ch)] = v
@@ -150,6 +154,36 @@ def make_batch(length=1_000_000, depth=30, read_len=150, seed=2, ref=None, ref_s
                 cigar=cigar, seq4=np.ascontiguousarray(seq4), qual=np.ascontiguousarray(qual.reshape(-1)),
                 tid=tid, tid_len=length, tid_name=tid_name, ref=ref if with_ref else None, ref_beg=0, ref_len=length,
                 pair_id=pair_id, read_len=L, ref_full=ref)
+
+
+def make_region(length, depth=30, read_len=150, seed=2, chunk=1_000_000, with_ref=False, tid_name='chr1', **kw):
+    """A `length`-bp window built from independent `chunk`-sized pieces (bounded generator memory).
+    Reads never cross a chunk edge, so the concatenation stays coordinate sorted."""
+    parts, off = [], 0
+    i = 0
+    while off < length:
+        ln = min(chunk, length - off)
+        parts.append((off, make_batch(length=ln, depth=depth, read_len=read_len, seed=seed * 1000 + i, ref_seed=seed * 1000 + i + 500,
+                                      with_ref=True, tid_name=tid_name, **kw)))
+        off += ln; i += 1
+    out = {}
+    nread = np.cumsum([0] + [len(p['pos']) for _, p in parts])
+    ncig = np.cumsum([0] + [len(p['cigar']) for _, p in parts])
+    nq = np.cumsum([0] + [len(p['qual']) for _, p in parts])
+    npair = np.cumsum([0] + [int(p['pair_id'].max()) + 1 if len(p['pair_id']) else 0 for _, p in parts])
+    cat = lambda key, add=None: np.concatenate([(p[key] + (add[i] if add is not None else 0)).astype(p[key].dtype) for i, (_, p) in enumerate(parts)])
+    offs = [o for o, _ in parts]
+    out['pos'] = cat('pos', offs); out['mpos'] = cat('mpos', offs)
+    for k_ in ('flag', 'mapq', 'l_qseq', 'n_cigar', 'mtid', 'isize', 'cigar', 'seq4', 'qual'):
+        out[k_] = cat(k_)
+    out['cigar_off'] = cat('cigar_off', [np.uint64(x) for x in ncig[:-1]]); out['qual_off'] = cat('qual_off', [np.uint64(x) for x in nq[:-1]])
+    out['prev_same_name'] = np.concatenate([np.where(p['prev_same_name'] >= 0, p['prev_same_name'] + nread[i], -1) for i, (_, p) in enumerate(parts)])
+    out['pair_id'] = cat('pair_id', list(npair[:-1]))
+    out['rbits'] = (_name_odd(out['pair_id']) * 2).astype(np.uint8)
+    out['file_start'] = np.array([0, nread[-1]], dtype=np.int64)
+    ref = np.concatenate([p['ref_full'] for _, p in parts])
+    out.update(tid=0, tid_len=length, tid_name=tid_name, ref=ref if with_ref else None, ref_beg=0, ref_len=length, read_len=read_len, ref_full=ref)
+    return out
 
 
 def algorithmic_bytes_in(soa, overlap=True):
