@@ -53,19 +53,46 @@ __device__ __forceinline__ void st_release_u64(uint64_t *p, uint64_t v)
 #define ST_FLAG(w) ((w) >> 62)
 #define ST_VAL(w) ((w) & 0x3fffffffffffffffULL)
 
-// decoupled look-back (sum): returns the exclusive prefix of tile `t`
+// status words are self-contained (flag + value in one 64-bit word), so polling
+// needs no acquire: relaxed gpu-scope accesses go to L2 and, unlike ld.acquire,
+// do not invalidate the SM's L1 (CCTL.IVALL) under the feet of the other warps.
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t *p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t *p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// decoupled look-back (sum), executed by ONE FULL WARP: 32 predecessors are
+// inspected per round.  Returns the exclusive prefix of tile `t` (all lanes).
 __device__ uint64_t lookback_sum(uint64_t *st, int t, uint64_t agg)
 {
-    if (t == 0) { st_release_u64(&st[0], (2ULL << 62) | agg); return 0; }
-    st_release_u64(&st[t], (1ULL << 62) | agg);
+    const int lane = threadIdx.x & 31;
+    if (t == 0) { if (lane == 0) st_relaxed_u64(&st[0], (2ULL << 62) | agg); return 0; }
+    if (lane == 0) st_relaxed_u64(&st[t], (1ULL << 62) | agg);
     uint64_t excl = 0;
-    for (int j = t - 1;; --j) {
+    for (int base = t - 1;; base -= 32) {
+        const int j = base - lane;
         uint64_t w;
-        while (ST_FLAG(w = ld_acquire_u64(&st[j])) == 0) { __nanosleep(20); }
-        excl += ST_VAL(w);
-        if (ST_FLAG(w) == 2) break;
+        unsigned m2, need;
+        for (;;) {
+            w = j >= 0 ? ld_relaxed_u64(&st[j]) : (2ULL << 62);      // before tile 0: inclusive prefix 0
+            m2 = __ballot_sync(0xffffffffu, ST_FLAG(w) == 2);
+            need = m2 ? ((2u << (__ffs(m2) - 1)) - 1u) : 0xffffffffu;  // lanes up to the nearest inclusive prefix
+            if ((__ballot_sync(0xffffffffu, ST_FLAG(w) == 0) & need) == 0) break;
+            __nanosleep(40);
+        }
+        uint64_t x = ((need >> lane) & 1u) ? ST_VAL(w) : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        excl += x;
+        if (m2) break;
     }
-    st_release_u64(&st[t], (2ULL << 62) | (excl + agg));
+    if (lane == 0) st_relaxed_u64(&st[t], (2ULL << 62) | (excl + agg));
     return excl;
 }
 
@@ -135,16 +162,16 @@ __global__ void k_scan_max(const int32_t *in, int32_t *out, int64_t n, uint64_t 
         // publish aggregate / look back (values biased to unsigned)
         const uint64_t agg = (uint64_t)((int64_t)run - INT32_MIN);
         uint64_t excl = 0;
-        if (t == 0) st_release_u64(&st[0], (2ULL << 62) | agg);
+        if (t == 0) st_relaxed_u64(&st[0], (2ULL << 62) | agg);
         else {
-            st_release_u64(&st[t], (1ULL << 62) | agg);
+            st_relaxed_u64(&st[t], (1ULL << 62) | agg);
             for (int j = t - 1;; --j) {
                 uint64_t wv;
-                while (ST_FLAG(wv = ld_acquire_u64(&st[j])) == 0) { __nanosleep(20); }
+                while (ST_FLAG(wv = ld_relaxed_u64(&st[j])) == 0) { __nanosleep(20); }
                 { const uint64_t pv = ST_VAL(wv); if (pv > excl) excl = pv; }
                 if (ST_FLAG(wv) == 2) break;
             }
-            st_release_u64(&st[t], (2ULL << 62) | (excl > agg ? excl : agg));
+            st_relaxed_u64(&st[t], (2ULL << 62) | (excl > agg ? excl : agg));
         }
         s_excl = (int32_t)((int64_t)excl + INT32_MIN);
     }
@@ -207,9 +234,9 @@ __device__ __forceinline__ void text_tile(const Fmt &fmt, int32_t ncols, char *o
     uint32_t len = c < ncols ? fmt.size(c, stt) : 0;
     uint32_t total;
     const uint32_t off = block_excl_scan<TILE>(len, s_ws, total);
-    if (threadIdx.x == 0) {
-        s_base = lookback_sum(status, t, total);
-        if (t == (int)gridDim.x - 1) *total_out = s_base + total;
+    if (threadIdx.x < 32) {
+        const uint64_t b = lookback_sum(status, t, total);
+        if (threadIdx.x == 0) { s_base = b; if (t == (int)gridDim.x - 1) *total_out = b + total; }
     }
     __syncthreads();
     const uint64_t base = s_base;
@@ -362,7 +389,7 @@ __global__ void k_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int32_t n, 
     const int32_t i = t * T + (int32_t)threadIdx.x;
     uint32_t v = i < n ? in[i] : 0, total;
     uint32_t off = block_excl_scan<T>(v, s_ws, total);
-    if (threadIdx.x == 0) s_base = lookback_sum(st, t, total);
+    if (threadIdx.x < 32) { const uint64_t b = lookback_sum(st, t, total); if (threadIdx.x == 0) s_base = b; }
     __syncthreads();
     if (i < n) out[i] = s_base + off;
     if (i == n - 1) out[n] = s_base + off + v;
@@ -412,7 +439,7 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     }
     cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
     cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
-    e->smem_text = 40 * 1024;
+    e->smem_text = 24 * 1024;
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
     cudaFuncSetAttribute(k_mpileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);

@@ -16,7 +16,7 @@ struct b200_engine {
     char err[512];
     int64_t launches = 0;
     double last_kernel_ms = 0, last_stage_ms = 0;
-    uint32_t smem_text = 40 * 1024;
+    uint32_t smem_text = 24 * 1024;
     int use_tma = 1;
 
     // raw SoA image of the staged records

@@ -30,7 +30,7 @@ namespace plp {
 enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X };
 
 // 32-byte read descriptor built on the device by the read stage
-struct ReadDesc {
+struct alignas(16) ReadDesc {
     int32_t rpos;      // leftmost column, relative to the window base
     int32_t rend;      // one past the last column the read can appear in (== rpos: never)
     uint64_t qoff;     // offset of qual[0]; nibble offset of the first base
@@ -42,6 +42,19 @@ struct ReadDesc {
     int32_t qstart;    // RD_SIMPLE: query index aligned to rpos
 };
 enum { RD_REV = 1, RD_SIMPLE = 2 };
+
+// one descriptor = two 16-byte words; on the device they go through the read-only path
+PLP_HD ReadDesc load_desc(const ReadDesc *p)
+{
+#if defined(__CUDA_ARCH__)
+    union { uint4 w[2]; ReadDesc d; } u;
+    u.w[0] = __ldg(reinterpret_cast<const uint4 *>(p));
+    u.w[1] = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+    return u.d;
+#else
+    return *p;
+#endif
+}
 
 struct View {
     const ReadDesc *desc;
@@ -78,15 +91,26 @@ struct Ent {
     uint8_t is_del, is_refskip, is_head, is_tail;
 };
 
+PLP_HD int ndigits32(uint32_t v)
+{
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6
+         : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
 PLP_HD int ndigits(uint64_t v)
 {
+    if (v <= 0xffffffffull) return ndigits32((uint32_t)v);
     int n = 1;
     while (v >= 10) { v /= 10; ++n; }
     return n;
 }
 PLP_HD int put_u64(char *p, uint64_t v)
 {
-    int n = ndigits(v);
+    const int n = ndigits(v);
+    if (v <= 0xffffffffull) {
+        uint32_t w = (uint32_t)v;
+        for (int i = n - 1; i >= 0; --i) { const uint32_t q = w / 10u; p[i] = (char)('0' + (w - q * 10u)); w = q; }
+        return n;
+    }
     for (int i = n - 1; i >= 0; --i) { p[i] = (char)('0' + v % 10); v /= 10; }
     return n;
 }
@@ -319,13 +343,27 @@ PLP_HD void mp_file_size(const View &v, const MpConf &cf, int f, int tile, int32
 {
     s.nplp = 0; s.cnt = 0; s.seq_len = 0; s.bp_len = 0; s.bp5_len = 0;
     const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
+    const uint32_t ends = cf.no_ends ? 0u : 1u;
     for (int32_t i = lo_; i < hi_; ++i) {
-        const ReadDesc d = v.desc[i];
-        if (c < d.rpos || c >= d.rend) continue;
+        const ReadDesc d = load_desc(v.desc + i);
+        const uint32_t rel = (uint32_t)(c - d.rpos);
+        if (rel >= (uint32_t)(d.rend - d.rpos)) continue;
+        ++s.nplp;
+        if (d.fl & RD_SIMPLE) {
+            // the common case ([S]<n>M[S]): one base, no indel text; 2 extra bytes at the read's
+            // first column ("^" + mapq), 1 at its last ("$")
+            const int32_t qpos = d.qstart + (int32_t)rel;
+            const int q = qpos < d.l_qseq ? (int)v.qual[d.qoff + (uint64_t)qpos] : 0;
+            if (q < cf.min_baseQ) continue;
+            ++s.cnt;
+            s.seq_len += 1u + (ends & (uint32_t)(rel == 0)) * 2u + (ends & (uint32_t)(c == d.rend - 1));
+            if (cf.out_qpos) s.bp_len += (uint32_t)ndigits32((uint32_t)(qpos + 1)) + 1;
+            if (cf.out_qpos5) { const int32_t q5 = (d.fl & RD_REV) ? d.l_qseq - qpos : qpos + 1; s.bp5_len += (uint32_t)(q5 < 0 ? 1 + ndigits32((uint32_t)(-q5)) : ndigits32((uint32_t)q5)) + 1; }
+            continue;
+        }
         const uint32_t *cg = v.cigar + d.cig_off;
         Ent e;
         resolve(v, d, c, e);
-        ++s.nplp;
         if (ent_qual(v, d, e) < cf.min_baseQ) continue;
         ++s.cnt;
         s.seq_len += (uint32_t)mp_entry_size(cf, d, cg, e);
@@ -384,19 +422,42 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
         if (cf.out_qpos5) *pb5++ = '\t';
         const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
         int n = 0;
+        // reference base of this column, once (bam_plcmd.c:74-80)
+        int rb = -1;
+        if (v.ref) {
+            rb = 15;
+            if ((int64_t)c < v.ref_len_rel) { const int64_t ri = (int64_t)c - v.ref_off; if (ri >= 0 && ri < v.ref_n) rb = nt16_of((unsigned char)v.ref[ri]); }
+        }
         for (int32_t i = lo_; i < hi_; ++i) {
-            const ReadDesc d = v.desc[i];
-            if (c < d.rpos || c >= d.rend) continue;
-            const uint32_t *cg = v.cigar + d.cig_off;
-            Ent e;
-            resolve(v, d, c, e);
-            int q = ent_qual(v, d, e);
-            if (q < cf.min_baseQ) continue;
-            ps += mp_entry_write(v, cf, d, cg, e, c, ps);
+            const ReadDesc d = load_desc(v.desc + i);
+            const uint32_t rel = (uint32_t)(c - d.rpos);
+            if (rel >= (uint32_t)(d.rend - d.rpos)) continue;
+            int q, qpos1; int32_t q5;
+            if (d.fl & RD_SIMPLE) {
+                const int32_t qpos = d.qstart + (int32_t)rel;
+                const bool in = qpos < d.l_qseq;
+                q = in ? (int)v.qual[d.qoff + (uint64_t)qpos] : 0;
+                if (q < cf.min_baseQ) continue;
+                const bool rev = d.fl & RD_REV;
+                if (!cf.no_ends && rel == 0) { *ps++ = '^'; *ps++ = (char)(d.mapq > 93 ? 126 : d.mapq + 33); }
+                int ch = in ? base4(v.seq4, d.qoff, qpos) : 15;
+                if (ch == rb) ch = 0;
+                *ps++ = rev ? ",acmgrsvtwyhkdbn"[ch] : ".ACMGRSVTWYHKDBN"[ch];
+                if (!cf.no_ends && c == d.rend - 1) *ps++ = '$';
+                qpos1 = qpos + 1; q5 = rev ? d.l_qseq - qpos : qpos + 1;
+            } else {
+                const uint32_t *cg = v.cigar + d.cig_off;
+                Ent e;
+                resolve(v, d, c, e);
+                q = ent_qual(v, d, e);
+                if (q < cf.min_baseQ) continue;
+                ps += mp_entry_write(v, cf, d, cg, e, c, ps);
+                qpos1 = e.qpos + 1; q5 = qpos5_of(d, e);
+            }
             *pq++ = (char)(q + 33 < 126 ? q + 33 : 126);
             if (cf.out_mapq) { int m = d.mapq + 33; *pm++ = (char)(m > 126 ? 126 : m); }
-            if (cf.out_qpos) { if (n) *pb++ = ','; pb += put_i32(pb, e.qpos + 1); }
-            if (cf.out_qpos5) { if (n) *pb5++ = ','; pb5 += put_i32(pb5, qpos5_of(d, e)); }
+            if (cf.out_qpos) { if (n) *pb++ = ','; pb += put_i32(pb, qpos1); }
+            if (cf.out_qpos5) { if (n) *pb5++ = ','; pb5 += put_i32(pb5, q5); }
             ++n;
         }
     }
@@ -458,7 +519,7 @@ PLP_HD void dp_file_column(const View &v, const DpConf &cf, int f, int tile, int
     o.depth = 0; o.spanned = false;
     const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
     for (int32_t i = lo_; i < hi_; ++i) {
-        const ReadDesc d = v.desc[i];
+        const ReadDesc d = load_desc(v.desc + i);
         if (c < d.rpos || c >= d.rend) continue;
         o.spanned = true;
         const int32_t clip = v.clip ? v.clip[i] : INT32_MIN;
@@ -492,7 +553,7 @@ PLP_HD void cv_column(const View &v, int32_t min_baseQ, int tile, int32_t c, CvC
         const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
         int32_t dpos = 0;
         for (int32_t i = lo_; i < hi_; ++i) {
-            const ReadDesc d = v.desc[i];
+            const ReadDesc d = load_desc(v.desc + i);
             if (c < d.rpos || c >= d.rend) continue;
             Ent e;
             resolve(v, d, c, e);
