@@ -267,6 +267,70 @@ __device__ __forceinline__ void text_tile(const Fmt &fmt, int32_t ncols, char *o
     }
 }
 
+// ---- two-launch variant: no inter-CTA dependency at all --------------------
+// (1) k_*_size: every thread sizes its line; per-column {len,state} and the
+//     tile total go to HBM (16-24 B per column, small next to the text itself);
+// (2) a scan of the tile totals gives each tile its byte offset;
+// (3) k_*_write: the tile formats its lines into shared memory, already laid
+//     out with the destination's 16-byte phase, and leaves through one TMA bulk
+//     store.  The chained single-launch variant above waits inside the kernel
+//     for predecessor tiles; this one never waits.
+template <class Fmt>
+__device__ __forceinline__ void text_size_tile(const Fmt &fmt, int32_t ncols, uint32_t *len_out, typename Fmt::State *st_out,
+                                               uint32_t *tile_total)
+{
+    __shared__ uint32_t s_ws[TILE / 32];
+    const int32_t c = (int32_t)blockIdx.x * TILE + (int32_t)threadIdx.x;
+    typename Fmt::State stt;
+    uint32_t len = 0;
+    if (c < ncols) { len = fmt.size(c, stt); len_out[c] = len; st_out[c] = stt; }
+    uint32_t x = len;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) s_ws[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int k = 0; k < TILE / 32; ++k) t += s_ws[k]; tile_total[blockIdx.x] = t; }
+}
+
+template <class Fmt>
+__device__ __forceinline__ void text_write_tile(const Fmt &fmt, int32_t ncols, const uint32_t *len_in, const typename Fmt::State *st_in,
+                                                const uint64_t *tile_base, char *out, uint32_t smem_cap, int use_tma)
+{
+    extern __shared__ __align__(16) char s_text[];
+    __shared__ uint32_t s_ws[TILE / 32];
+    const int32_t c = (int32_t)blockIdx.x * TILE + (int32_t)threadIdx.x;
+    typename Fmt::State stt;
+    uint32_t len = 0;
+    if (c < ncols) { len = len_in[c]; if (len) stt = st_in[c]; }
+    uint32_t total;
+    const uint32_t off = block_excl_scan<TILE>(len, s_ws, total);
+    if (total == 0) return;
+    const uint64_t base = tile_base[blockIdx.x];
+    const uint32_t phase = (uint32_t)(base & 15);
+    if (total + phase <= smem_cap) {
+        char *sb = s_text + phase;
+        if (len) fmt.write(c, stt, sb + off);
+        __syncthreads();
+        char *g = out + base;
+        const uint32_t head = min(total, (16u - phase) & 15u);
+        const uint32_t body = (total - head) & ~15u;
+        const uint32_t tail = total - head - body;
+        if (threadIdx.x < head) g[threadIdx.x] = sb[threadIdx.x];
+        if (threadIdx.x < tail) g[head + body + threadIdx.x] = sb[head + body + threadIdx.x];
+        if (body) {
+            if (use_tma) {
+                if (threadIdx.x == 0) bulk_store_s2g(g + head, sb + head, body);
+            } else {
+                const uint4 *src = reinterpret_cast<const uint4 *>(sb + head);
+                uint4 *dst = reinterpret_cast<uint4 *>(g + head);
+                for (uint32_t i = threadIdx.x; i < body / 16; i += TILE) dst[i] = src[i];
+            }
+        }
+    } else if (len) {
+        fmt.write(c, stt, out + base + off);
+    }
+}
+
 struct MpFmt {
     View v; MpConf cf;
     typedef MpFileSz State;
@@ -278,6 +342,16 @@ __global__ void __launch_bounds__(TILE) k_mpileup(MpFmt fmt, char *out, uint64_t
                                                   unsigned long long *total_out, uint32_t smem_cap, int use_tma)
 {
     text_tile(fmt, fmt.v.ncols, out, status, ticket, total_out, smem_cap, use_tma);
+}
+
+__global__ void __launch_bounds__(TILE) k_mpileup_size(MpFmt fmt, uint32_t *len, MpFileSz *st, uint32_t *tile_total)
+{
+    text_size_tile(fmt, fmt.v.ncols, len, st, tile_total);
+}
+__global__ void __launch_bounds__(TILE) k_mpileup_write(MpFmt fmt, const uint32_t *len, const MpFileSz *st, const uint64_t *tile_base,
+                                                        char *out, uint32_t smem_cap, int use_tma)
+{
+    text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
 }
 
 // depth rows "name\tpos(\tdepth)*\n" (bam2depth.c:234-244)
@@ -316,6 +390,16 @@ __global__ void __launch_bounds__(TILE) k_depth(DpFmt fmt, char *out, uint64_t *
                                                 unsigned long long *total_out, uint32_t smem_cap, int use_tma)
 {
     text_tile(fmt, fmt.v.ncols, out, status, ticket, total_out, smem_cap, use_tma);
+}
+
+__global__ void __launch_bounds__(TILE) k_depth_size(DpFmt fmt, uint32_t *len, DpFmt::State *st, uint32_t *tile_total)
+{
+    text_size_tile(fmt, fmt.v.ncols, len, st, tile_total);
+}
+__global__ void __launch_bounds__(TILE) k_depth_write(DpFmt fmt, const uint32_t *len, const DpFmt::State *st, const uint64_t *tile_base,
+                                                      char *out, uint32_t smem_cap, int use_tma)
+{
+    text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
 }
 
 // coverage column sums (coverage.c:622-660)
@@ -442,6 +526,9 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     e->smem_text = 24 * 1024;
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
+    s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
+    cudaFuncSetAttribute(k_mpileup_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
+    cudaFuncSetAttribute(k_depth_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_mpileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_depth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaMalloc((void **)&e->d_acc, sizeof(StageAcc));
@@ -664,8 +751,8 @@ static int upload_bed(b200_engine *e, const int64_t *bb, const int64_t *be, int 
     return 0;
 }
 
-template <class Fmt, class K>
-static int run_text(b200_engine *e, K kernel, const Fmt &fmt, uint64_t bound, char *out, size_t out_cap, size_t *out_len)
+template <class Fmt, class K, class KS, class KW>
+static int run_text(b200_engine *e, K kernel, KS k_size, KW k_write, const Fmt &fmt, uint64_t bound, char *out, size_t out_cap, size_t *out_len)
 {
     const int32_t ncols = fmt.v.ncols;
     const int nt = (ncols + TILE - 1) / TILE;
@@ -673,15 +760,34 @@ static int run_text(b200_engine *e, K kernel, const Fmt &fmt, uint64_t bound, ch
     e->last_kernel_ms = 0;
     if (nt == 0) return 0;
     ENSURE(out, (size_t)bound + 64);
-    ENSURE(status, (size_t)nt + 1);
-    CK(cudaMemsetAsync(e->status, 0, ((size_t)nt + 1) * 8, e->stream));
-    CK(cudaMemsetAsync(e->d_misc, 0, 16, e->stream));
-    CK(cudaEventRecord(e->ev0, e->stream));
-    kernel<<<nt, TILE, e->smem_text + 16, e->stream>>>(fmt, e->out, e->status, (uint32_t *)e->d_misc, e->d_misc + 1, e->smem_text, e->use_tma);
-    e->launches++;
-    CK(cudaEventRecord(e->ev1, e->stream));
     unsigned long long total = 0;
-    CK(cudaMemcpyAsync(&total, e->d_misc + 1, 8, cudaMemcpyDeviceToHost, e->stream));
+    if (e->chained) {
+        ENSURE(status, (size_t)nt + 1);
+        CK(cudaMemsetAsync(e->status, 0, ((size_t)nt + 1) * 8, e->stream));
+        CK(cudaMemsetAsync(e->d_misc, 0, 16, e->stream));
+        CK(cudaEventRecord(e->ev0, e->stream));
+        kernel<<<nt, TILE, e->smem_text + 16, e->stream>>>(fmt, e->out, e->status, (uint32_t *)e->d_misc, e->d_misc + 1, e->smem_text, e->use_tma);
+        e->launches++;
+        CK(cudaEventRecord(e->ev1, e->stream));
+        CK(cudaMemcpyAsync(&total, e->d_misc + 1, 8, cudaMemcpyDeviceToHost, e->stream));
+    } else {
+        typedef typename Fmt::State State;
+        ENSURE(col_n, (size_t)ncols + 1);                                   // per-column line length
+        const size_t st_words = ((size_t)ncols * sizeof(State) + 7) / 8 + 1;
+        ENSURE(col_state, st_words);                                        // per-column formatter state
+        ENSURE(tile_total, (size_t)nt + 1); ENSURE(col_off, (size_t)nt + 2);
+        const int nb = nblk(nt, 256);
+        ENSURE(status, (size_t)nb + 1);
+        CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
+        CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
+        CK(cudaEventRecord(e->ev0, e->stream));
+        k_size<<<nt, TILE, 0, e->stream>>>(fmt, e->col_n, (State *)e->col_state, e->tile_total); e->launches++;
+        k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
+        k_write<<<nt, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const State *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        e->launches++;
+        CK(cudaEventRecord(e->ev1, e->stream));
+        CK(cudaMemcpyAsync(&total, e->col_off + nt, 8, cudaMemcpyDeviceToHost, e->stream));
+    }
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
@@ -708,7 +814,7 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     fmt.cf.out_qpos5 = c->out_qpos5; fmt.cf.n_star_cols = c->n_star_cols;
     const int per = 2 + (c->out_mapq ? 1 : 0) + (c->out_qpos ? 12 : 0) + (c->out_qpos5 ? 13 : 0);
     const uint64_t bound = e->text_bound(per, 1 + 2 * (3 + c->n_star_cols)) ;
-    return run_text(e, k_mpileup, fmt, bound, out, out_cap, out_len);
+    return run_text(e, k_mpileup, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
 }
 
 extern "C" int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, char *out, size_t out_cap, size_t *out_len)
@@ -721,7 +827,7 @@ extern "C" int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, cha
     fmt.cf.min_qual = c->min_qual; fmt.cf.count_del = c->count_del; fmt.cf.all = c->all;
     const uint64_t ncols = (uint64_t)fmt.v.ncols;
     const uint64_t bound = ncols * (e->name.size() + 1 + 20 + (uint64_t)e->n_files * 12 + 1) + 64;
-    return run_text(e, k_depth, fmt, bound, out, out_cap, out_len);
+    return run_text(e, k_depth, k_depth_size, k_depth_write, fmt, bound, out, out_cap, out_len);
 }
 
 extern "C" int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b200_coverage_sums_t *sums)

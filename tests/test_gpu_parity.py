@@ -138,7 +138,8 @@ def test_c2_size_properties():
     from samtools_b200 import engine, synth
     soa = noref(synth.make_batch(length=1_000_000, depth=30, seed=2))
     digests = {}
-    for tag, env in (('tma', {'B200_PLP_TMA': '1'}), ('vec', {'B200_PLP_TMA': '0'}), ('direct', {'B200_PLP_SMEM_TEXT': '1024'})):
+    for tag, env in (('tma', {'B200_PLP_TMA': '1'}), ('vec', {'B200_PLP_TMA': '0'}), ('direct', {'B200_PLP_SMEM_TEXT': '1024'}),
+                     ('chained', {'B200_PLP_CHAINED': '1'}), ('chained_direct', {'B200_PLP_CHAINED': '1', 'B200_PLP_SMEM_TEXT': '1024'})):
         os.environ.update(env)
         e = engine.Engine(0)
         e.stage(soa, engine.default_stage_conf(engine.MODE_MPILEUP))
@@ -155,4 +156,4 @@ def test_c2_size_properties():
             # depth column sums to the number of kept (read, column) pairs that pass -Q13; positions ascend
             pos = np.array([int(l.split(b'\t', 2)[1]) for l in lines[:-1:997]])
             assert (np.diff(pos) > 0).all()
-    assert len(set(digests.values())) == 1, digests   # shared-memory/TMA, vector-store and direct paths agree
+    assert len(set(digests.values())) == 1, digests   # two-launch / chained single-launch, TMA / vector / direct-to-HBM stores all agree
