@@ -183,7 +183,11 @@ __global__ void k_scan_max(const int32_t *in, int32_t *out, int64_t n, uint64_t 
     for (int j = 0; j < IPT; ++j) if (base + j < n) out[base + j] = max(pre, v[j]);
 }
 
-// per 32-column group: the [lo,hi) slice of each file's reads that can cover it
+// per 32-column group: the [lo,hi) slice of each file's reads that can cover it.
+// lo is the later of (a) the first read whose running max end exceeds the group start and
+// (b) the first read starting within kReach columns of it; reads before (b) that still
+// reach the group are listed separately (k_ovf_*), so one spliced read cannot widen the
+// slice of every group under it.
 __global__ void k_ranges(const ReadDesc *desc, const int32_t *pmax, const int64_t *file_start, int n_files,
                          int32_t n_groups, int32_t *glo, int32_t *ghi, int *max_range)
 {
@@ -194,14 +198,58 @@ __global__ void k_ranges(const ReadDesc *desc, const int32_t *pmax, const int64_
     const int32_t c0 = g * 32, c1 = c0 + 31;
     int64_t lo = fs, hi = fe;
     while (lo < hi) { int64_t m = (lo + hi) >> 1; if (pmax[m] > c0) hi = m; else lo = m + 1; }   // first read whose running max end exceeds c0
-    const int64_t first = lo;
+    int64_t first = lo;
+    lo = first; hi = fe;
+    while (lo < hi) { int64_t m = (lo + hi) >> 1; if (desc[m].rpos > c0 - kReach) hi = m; else lo = m + 1; }  // first read within reach
+    if (lo > first) first = lo;
     lo = first; hi = fe;
     while (lo < hi) { int64_t m = (lo + hi) >> 1; if (desc[m].rpos > c1) hi = m; else lo = m + 1; }  // first read starting beyond c1
-    glo[idx] = (int32_t)first;
     const int64_t last = lo > first ? lo : first;
+    glo[idx] = (int32_t)first;
     ghi[idx] = (int32_t)last;
     atomicMax(max_range, (int)(last - first));
 }
+
+// far-reaching reads: read i is listed for group g when 32g >= rpos_i + kReach and 32g < rend_i
+__device__ __forceinline__ void ovf_span(const ReadDesc &d, int32_t n_groups, int32_t &g0, int32_t &g1)
+{
+    const int64_t a = (int64_t)d.rpos + kReach;
+    g0 = (int32_t)(a <= 0 ? 0 : (a + 31) >> 5);
+    g1 = d.rend > 0 ? (d.rend - 1) >> 5 : -1;
+    if (g1 >= n_groups) g1 = n_groups - 1;
+}
+__global__ void k_ovf_count(const ReadDesc *desc, const int64_t *file_start, int n_files, int64_t n, int32_t n_groups, uint32_t *cnt)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ReadDesc d = desc[i];
+    if ((int64_t)d.rend - d.rpos <= kReach) return;
+    int f = 0; while (f + 1 < n_files && i >= file_start[f + 1]) ++f;
+    int32_t g0, g1; ovf_span(d, n_groups, g0, g1);
+    for (int32_t g = g0; g <= g1; ++g) atomicAdd(&cnt[(int64_t)f * n_groups + g], 1u);
+}
+__global__ void k_ovf_fill(const ReadDesc *desc, const int64_t *file_start, int n_files, int64_t n, int32_t n_groups,
+                           const int32_t *off, uint32_t *cursor, int32_t *idx)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ReadDesc d = desc[i];
+    if ((int64_t)d.rend - d.rpos <= kReach) return;
+    int f = 0; while (f + 1 < n_files && i >= file_start[f + 1]) ++f;
+    int32_t g0, g1; ovf_span(d, n_groups, g0, g1);
+    for (int32_t g = g0; g <= g1; ++g) {
+        const int64_t k = (int64_t)f * n_groups + g;
+        idx[off[k] + (int32_t)atomicAdd(&cursor[k], 1u)] = (int32_t)i;
+    }
+}
+__global__ void k_ovf_sort(const int32_t *off, int32_t *idx, int64_t n_lists)   // lists are tiny: insertion sort restores file order
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_lists) return;
+    int32_t *a = idx + off[k]; const int32_t m = off[k + 1] - off[k];
+    for (int32_t i = 1; i < m; ++i) { const int32_t x = a[i]; int32_t j = i - 1; while (j >= 0 && a[j] > x) { a[j + 1] = a[j]; --j; } a[j + 1] = x; }
+}
+__global__ void k_scan_u32_excl_i32(const uint32_t *in, int32_t *out, int32_t n, uint64_t *st, uint32_t *ticket);
 
 // ============================== column stage =================================
 constexpr int TILE = 128;
@@ -434,9 +482,9 @@ __global__ void k_entries_count(View v, int f, uint32_t *col_n)
     const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= v.ncols) return;
     const int g = c >> 5;
-    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + g], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + g];
+    const ReadRange rr = read_range(v, f, g);
     uint32_t n = 0;
-    for (int32_t i = lo_; i < hi_; ++i) { const ReadDesc d = v.desc[i]; if (c >= d.rpos && c < d.rend) ++n; }
+    for (int32_t t_ = 0; t_ < rr.n; ++t_) { const ReadDesc d = v.desc[range_at(rr, t_)]; if (c >= d.rpos && c < d.rend) ++n; }
     col_n[c] = n;
 }
 __global__ void k_entries_fill(View v, int f, const uint64_t *col_off, b200_pileup1_t *ents, int64_t file_first)
@@ -444,9 +492,10 @@ __global__ void k_entries_fill(View v, int f, const uint64_t *col_off, b200_pile
     const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= v.ncols) return;
     const int g = c >> 5;
-    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + g], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + g];
+    const ReadRange rr = read_range(v, f, g);
     b200_pileup1_t *o = ents + col_off[c];
-    for (int32_t i = lo_; i < hi_; ++i) {
+    for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+        const int32_t i = range_at(rr, t_);
         const ReadDesc d = v.desc[i];
         if (c < d.rpos || c >= d.rend) continue;
         Ent e; resolve(v, d, c, e);
@@ -477,6 +526,23 @@ __global__ void k_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int32_t n, 
     __syncthreads();
     if (i < n) out[i] = s_base + off;
     if (i == n - 1) out[n] = s_base + off + v;
+}
+
+__global__ void k_scan_u32_excl_i32(const uint32_t *in, int32_t *out, int32_t n, uint64_t *st, uint32_t *ticket)
+{
+    constexpr int T = 256;
+    __shared__ uint32_t s_ws[T / 32];
+    __shared__ int s_tile; __shared__ uint64_t s_base;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int t = s_tile;
+    const int32_t i = t * T + (int32_t)threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0, total;
+    uint32_t off = block_excl_scan<T>(v, s_ws, total);
+    if (threadIdx.x < 32) { const uint64_t b = lookback_sum(st, t, total); if (threadIdx.x == 0) s_base = b; }
+    __syncthreads();
+    if (i < n) out[i] = (int32_t)(s_base + off);
+    if (i == n - 1) out[n] = (int32_t)(s_base + off + v);
 }
 
 // ============================== host side ====================================
@@ -690,6 +756,8 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
     } else {
         CK(cudaMemsetAsync(e->glo, 0, ((size_t)e->n_groups * e->n_files) * 4, e->stream));
         CK(cudaMemsetAsync(e->ghi, 0, ((size_t)e->n_groups * e->n_files) * 4, e->stream));
+        ENSURE(ovf_off, (size_t)e->n_groups * e->n_files + 2); ENSURE(ovf_idx, 1);
+        CK(cudaMemsetAsync(e->ovf_off, 0, ((size_t)e->n_groups * e->n_files + 2) * 4, e->stream));
         e->has_clip = false;
     }
     CK(cudaEventRecord(e->ev1, e->stream));
@@ -722,10 +790,28 @@ int build_ranges(b200_engine *e, int *max_range)
     const int64_t tot = (int64_t)e->n_groups * e->n_files;
     k_ranges<<<nblk(tot, 256), 256, 0, e->stream>>>(e->desc, e->pmax, e->file_start, e->n_files, e->n_groups, e->glo, e->ghi, (int *)(e->d_misc + 1));
     e->launches++;
+    // far-reaching reads per group
+    ENSURE(ovf_cnt, (size_t)tot + 1); ENSURE(ovf_off, (size_t)tot + 2);
+    CK(cudaMemsetAsync(e->ovf_cnt, 0, ((size_t)tot + 1) * 4, e->stream));
+    k_ovf_count<<<nblk(n, 256), 256, 0, e->stream>>>(e->desc, e->file_start, e->n_files, n, e->n_groups, e->ovf_cnt); e->launches++;
+    {
+        const int nb = nblk(tot, 256);
+        ENSURE(status, (size_t)nb + 1);
+        CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
+        CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
+        k_scan_u32_excl_i32<<<nb, 256, 0, e->stream>>>(e->ovf_cnt, e->ovf_off, (int32_t)tot, e->status, (uint32_t *)e->d_misc); e->launches++;
+    }
+    int32_t n_ovf = 0;
+    CK(cudaMemcpyAsync(&n_ovf, e->ovf_off + tot, 4, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaMemcpyAsync(max_range, e->d_misc + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    ENSURE(ovf_idx, (size_t)n_ovf + 1);
+    if (n_ovf > 0) {
+        CK(cudaMemsetAsync(e->ovf_cnt, 0, ((size_t)tot + 1) * 4, e->stream));
+        k_ovf_fill<<<nblk(n, 256), 256, 0, e->stream>>>(e->desc, e->file_start, e->n_files, n, e->n_groups, e->ovf_off, e->ovf_cnt, e->ovf_idx); e->launches++;
+        k_ovf_sort<<<nblk(tot, 256), 256, 0, e->stream>>>(e->ovf_off, e->ovf_idx, tot); e->launches++;
+    }
     CK(cudaGetLastError());
-    (void)n;
     return 0;
 }
 
@@ -736,7 +822,7 @@ static void fill_view(b200_engine *e, View &v, const int64_t *bed_beg, const int
     v.ref = e->has_ref ? e->ref : nullptr;
     v.ref_off = e->ref_beg - e->win_base; v.ref_n = e->ref_n; v.ref_len_rel = e->ref_len - e->win_base;
     v.n_files = e->n_files; v.file_start = e->file_start;
-    v.tile_lo = e->glo; v.tile_hi = e->ghi; v.n_tiles = e->n_groups; v.tile_cols = 32;
+    v.tile_lo = e->glo; v.tile_hi = e->ghi; v.ovf_off = e->ovf_off; v.ovf_idx = e->ovf_idx; v.n_tiles = e->n_groups; v.tile_cols = 32;
     v.win_base = e->win_base;
     v.ncols_all = all ? (int32_t)e->ncols_all : 0;
     v.ncols = (int32_t)(all ? std::max(e->ncols_cov, e->ncols_all) : e->ncols_cov);

@@ -29,7 +29,8 @@ struct b200_engine {
     DBUF(uint8_t, state); DBUF(int32_t, rlen); DBUF(plp::ReadDesc, desc); DBUF(int32_t, endv); DBUF(int32_t, pmax);
     DBUF(int32_t, glo); DBUF(int32_t, ghi); DBUF(uint64_t, status); DBUF(char, out);
     DBUF(int64_t, bed_beg); DBUF(int64_t, bed_end);
-    DBUF(uint32_t, col_n); DBUF(uint64_t, col_off); DBUF(uint64_t, col_state); DBUF(uint32_t, tile_total); DBUF(b200_pileup1_t, ents);
+    DBUF(uint32_t, col_n); DBUF(uint64_t, col_off); DBUF(uint64_t, col_state); DBUF(uint32_t, tile_total);
+    DBUF(uint32_t, ovf_cnt); DBUF(int32_t, ovf_off); DBUF(int32_t, ovf_idx); DBUF(b200_pileup1_t, ents);
     DBUF(int32_t, clip); DBUF(int64_t, next); DBUF(int32_t, cig_x); DBUF(int32_t, cig_y);
     DBUF(double, baq_f); DBUF(int32_t, baq_idx);
     DBUF(float, gl_out); DBUF(int32_t, gl_n); DBUF(uint32_t, gl_flag);
@@ -61,7 +62,7 @@ struct b200_engine {
     {
         void *ps[] = { pos, flag, mapq, l_qseq, n_cigar, cigar_off, qual_off, mtid, mpos, isize, prev, rbits, cigar, seq4, qual,
                        ref, dname, file_start, state, rlen, desc, endv, pmax, glo, ghi, status, out, bed_beg, bed_end, col_n,
-                       col_off, col_state, tile_total, ents, clip, next, cig_x, cig_y, baq_f, baq_idx, gl_out, gl_n, gl_flag, d_beta, d_fk, d_lhet, d_q2p, d_qthr };
+                       col_off, col_state, tile_total, ovf_cnt, ovf_off, ovf_idx, ents, clip, next, cig_x, cig_y, baq_f, baq_idx, gl_out, gl_n, gl_flag, d_beta, d_fk, d_lhet, d_q2p, d_qthr };
         for (void *p : ps) if (p) cudaFree(p);
     }
 };

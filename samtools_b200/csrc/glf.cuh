@@ -52,12 +52,12 @@ __global__ void k_gl_count(View v, int min_baseQ, uint32_t *draws, int32_t *nplp
     if (idx >= (int64_t)v.ncols * v.n_files) return;
     const int32_t c = (int32_t)(idx / v.n_files); const int f = (int)(idx % v.n_files);
     const int g = c >> 5;
-    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + g], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + g];
+    const ReadRange rr = read_range(v, f, g);
     int rb4 = 15;
     { const char rc = ref_char(v, c); rb4 = (v.ref && (int64_t)c < v.ref_len_rel) ? nt16_of((unsigned char)rc) : 15; }
     uint32_t n = 0, np = 0;
-    for (int32_t i = lo_; i < hi_; ++i) {
-        const ReadDesc d = v.desc[i];
+    for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+        const ReadDesc d = v.desc[range_at(rr, t_)];
         if (c < d.rpos || c >= d.rend) continue;
         ++np;
         uint16_t code; int q, b;
@@ -77,17 +77,17 @@ __global__ void __launch_bounds__(128) k_gl(View v, int min_baseQ, const uint64_
     if (idx >= (int64_t)v.ncols * v.n_files) return;
     const int32_t c = (int32_t)(idx / v.n_files); const int f = (int)(idx % v.n_files);
     const int g = c >> 5;
-    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + g], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + g];
+    const ReadRange rr = read_range(v, f, g);
     uint16_t *bs = s_b[wl];
     int rb4;
     { const char rc = ref_char(v, c); rb4 = (v.ref && (int64_t)c < v.ref_len_rel) ? nt16_of((unsigned char)rc) : 15; }
     int n = 0, nplp = 0;
     float qsum[4] = {0, 0, 0, 0};   // exact small integers, order-independent below 2^24
-    for (int32_t base = lo_; base < hi_; base += 32) {
-        const int32_t i = base + lane;
+    for (int32_t base = 0; base < rr.n; base += 32) {
+        const int32_t t_ = base + lane;
         bool ok = false, cov = false; uint16_t code = 0; int q = 0, b = 4;
-        if (i < hi_) {
-            const ReadDesc d = v.desc[i];
+        if (t_ < rr.n) {
+            const ReadDesc d = v.desc[range_at(rr, t_)];
             if (c >= d.rpos && c < d.rend) { cov = true; ok = gl_code(v, d, c, min_baseQ, rb4, code, q, b); }
         }
         const unsigned mk = __ballot_sync(0xffffffffu, ok);

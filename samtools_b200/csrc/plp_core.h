@@ -72,6 +72,8 @@ struct View {
     const int64_t *file_start; // [n_files+1]
     const int32_t *tile_lo;    // [n_files][n_tiles] first read to inspect
     const int32_t *tile_hi;    // [n_files][n_tiles] one past the last
+    const int32_t *ovf_off;    // [n_files*n_tiles+1] far-reaching reads that start before tile_lo but still cover the group
+    const int32_t *ovf_idx;    //   their read indices, ascending
     int32_t n_tiles;
     int32_t tile_cols;
     int64_t win_base;          // absolute coordinate of relative column 0
@@ -80,6 +82,25 @@ struct View {
     const char *name; int32_t name_len;
     const int64_t *bed_beg, *bed_end; int32_t n_bed; int32_t bed_active;
 };
+
+// Reads that can cover a 32-column group = far-reaching reads (index < lo, e.g. spliced or
+// long-deletion alignments; usually none) followed by the contiguous slice [lo,hi).  Both parts
+// are in file order and every index of the first part is below lo, so one pass over the
+// concatenation visits the covering reads in file order.
+constexpr int32_t kReach = 512;   // a read registers as far-reaching for groups starting >= rpos + kReach
+struct ReadRange { int32_t n_ovf, lo, n; const int32_t *ovf; };
+PLP_HD ReadRange read_range(const View &v, int f, int g)
+{
+    const int64_t k = (int64_t)f * v.n_tiles + g;
+    ReadRange r;
+    const int32_t o0 = v.ovf_off[k];
+    r.n_ovf = v.ovf_off[k + 1] - o0;
+    r.ovf = v.ovf_idx + o0;
+    r.lo = v.tile_lo[k];
+    r.n = r.n_ovf + (v.tile_hi[k] - r.lo);
+    return r;
+}
+PLP_HD int32_t range_at(const ReadRange &r, int32_t t) { return t < r.n_ovf ? r.ovf[t] : r.lo + (t - r.n_ovf); }
 
 struct MpConf {
     int32_t min_baseQ, all, rev_del, no_ins, no_del, no_ends, out_mapq, out_qpos, out_qpos5, n_star_cols;
@@ -342,9 +363,10 @@ PLP_HD int32_t qpos5_of(const ReadDesc &d, const Ent &e)
 PLP_HD void mp_file_size(const View &v, const MpConf &cf, int f, int tile, int32_t c, MpFileSz &s)
 {
     s.nplp = 0; s.cnt = 0; s.seq_len = 0; s.bp_len = 0; s.bp5_len = 0;
-    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
+    const ReadRange rr = read_range(v, f, tile);
     const uint32_t ends = cf.no_ends ? 0u : 1u;
-    for (int32_t i = lo_; i < hi_; ++i) {
+    for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+        const int32_t i = range_at(rr, t_);
         const ReadDesc d = load_desc(v.desc + i);
         const uint32_t rel = (uint32_t)(c - d.rpos);
         if (rel >= (uint32_t)(d.rend - d.rpos)) continue;
@@ -420,7 +442,7 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
         if (cf.out_mapq) *pm++ = '\t';
         if (cf.out_qpos) *pb++ = '\t';
         if (cf.out_qpos5) *pb5++ = '\t';
-        const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
+        const ReadRange rr = read_range(v, f, tile);
         int n = 0;
         // reference base of this column, once (bam_plcmd.c:74-80)
         int rb = -1;
@@ -428,7 +450,8 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
             rb = 15;
             if ((int64_t)c < v.ref_len_rel) { const int64_t ri = (int64_t)c - v.ref_off; if (ri >= 0 && ri < v.ref_n) rb = nt16_of((unsigned char)v.ref[ri]); }
         }
-        for (int32_t i = lo_; i < hi_; ++i) {
+        for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+        const int32_t i = range_at(rr, t_);
             const ReadDesc d = load_desc(v.desc + i);
             const uint32_t rel = (uint32_t)(c - d.rpos);
             if (rel >= (uint32_t)(d.rend - d.rpos)) continue;
@@ -517,8 +540,9 @@ struct DpCol { int32_t depth; bool spanned; };
 PLP_HD void dp_file_column(const View &v, const DpConf &cf, int f, int tile, int32_t c, DpCol &o)
 {
     o.depth = 0; o.spanned = false;
-    const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
-    for (int32_t i = lo_; i < hi_; ++i) {
+    const ReadRange rr = read_range(v, f, tile);
+    for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+        const int32_t i = range_at(rr, t_);
         const ReadDesc d = load_desc(v.desc + i);
         if (c < d.rpos || c >= d.rend) continue;
         o.spanned = true;
@@ -550,9 +574,10 @@ PLP_HD void cv_column(const View &v, int32_t min_baseQ, int tile, int32_t c, CvC
 {
     o.depth = 0; o.qbases = 0; o.sum_bq = 0; o.missing = 0; o.count_base = false;
     for (int f = 0; f < v.n_files; ++f) {
-        const int32_t lo_ = v.tile_lo[(int64_t)f * v.n_tiles + tile], hi_ = v.tile_hi[(int64_t)f * v.n_tiles + tile];
+        const ReadRange rr = read_range(v, f, tile);
         int32_t dpos = 0;
-        for (int32_t i = lo_; i < hi_; ++i) {
+        for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+        const int32_t i = range_at(rr, t_);
             const ReadDesc d = load_desc(v.desc + i);
             if (c < d.rpos || c >= d.rend) continue;
             Ent e;

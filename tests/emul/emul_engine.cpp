@@ -24,7 +24,7 @@ using namespace plp;
 struct b200_engine {
     std::string err, name;
     b200_batch_t b; b200_stage_conf_t cf;
-    std::vector<uint8_t> qual, mapq, state; std::vector<int32_t> rlen, endv, pmax, glo, ghi, clip, cig_x, cig_y; std::vector<ReadDesc> desc;
+    std::vector<uint8_t> qual, mapq, state; std::vector<int32_t> rlen, endv, pmax, glo, ghi, clip, cig_x, cig_y, ovf_off, ovf_idx; std::vector<ReadDesc> desc;
     std::vector<int64_t> next, bedb, bede;
     std::string ref;
     StageAcc acc;
@@ -70,13 +70,31 @@ static void build_ranges(b200_engine *e, int *max_range)
             const int32_t c0 = g * 32, c1 = c0 + 31;
             int64_t lo = fs, hi = fe;
             while (lo < hi) { int64_t m = (lo + hi) >> 1; if (e->pmax[(size_t)m] > c0) hi = m; else lo = m + 1; }
-            const int64_t first = lo;
+            int64_t first = lo;
             hi = fe;
+            while (lo < hi) { int64_t m = (lo + hi) >> 1; if (e->desc[(size_t)m].rpos > c0 - kReach) hi = m; else lo = m + 1; }
+            if (lo > first) first = lo;
+            lo = first; hi = fe;
             while (lo < hi) { int64_t m = (lo + hi) >> 1; if (e->desc[(size_t)m].rpos > c1) hi = m; else lo = m + 1; }
             const int64_t last = std::max(lo, first);
             e->glo[(size_t)f * e->n_groups + g] = (int32_t)first; e->ghi[(size_t)f * e->n_groups + g] = (int32_t)last;
             *max_range = std::max(*max_range, (int)(last - first));
         }
+    // far-reaching reads per group (same rule as k_ovf_*)
+    std::vector<std::vector<int32_t>> lists((size_t)e->n_groups * b.n_files);
+    for (int f = 0; f < b.n_files; ++f)
+        for (int64_t i = b.file_start[f]; i < b.file_start[f + 1]; ++i) {
+            const ReadDesc &d = e->desc[(size_t)i];
+            if ((int64_t)d.rend - d.rpos <= kReach) continue;
+            const int64_t a = (int64_t)d.rpos + kReach;
+            int32_t g0 = (int32_t)(a <= 0 ? 0 : (a + 31) >> 5), g1 = d.rend > 0 ? (d.rend - 1) >> 5 : -1;
+            if (g1 >= e->n_groups) g1 = e->n_groups - 1;
+            for (int32_t g = g0; g <= g1; ++g) lists[(size_t)f * e->n_groups + g].push_back((int32_t)i);
+        }
+    e->ovf_off.assign(lists.size() + 2, 0); e->ovf_idx.clear();
+    for (size_t k = 0; k < lists.size(); ++k) { e->ovf_off[k] = (int32_t)e->ovf_idx.size(); e->ovf_idx.insert(e->ovf_idx.end(), lists[k].begin(), lists[k].end()); }
+    e->ovf_off[lists.size()] = (int32_t)e->ovf_idx.size(); e->ovf_off[lists.size() + 1] = (int32_t)e->ovf_idx.size();
+    e->ovf_idx.push_back(0);
 }
 
 int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t *cf, b200_stage_stats_t *stats)
@@ -158,7 +176,7 @@ static void fill_view(b200_engine *e, View &v, const int64_t *bb, const int64_t 
     v.clip = e->has_clip ? e->clip.data() : nullptr;
     v.ref = (b.ref && b.ref_len > 0) ? e->ref.data() : nullptr;
     v.ref_off = b.ref_beg - e->win_base; v.ref_n = b.ref_n; v.ref_len_rel = (v.ref ? b.ref_len : 0) - e->win_base;
-    v.n_files = b.n_files; v.file_start = b.file_start; v.tile_lo = e->glo.data(); v.tile_hi = e->ghi.data();
+    v.n_files = b.n_files; v.file_start = b.file_start; v.tile_lo = e->glo.data(); v.tile_hi = e->ghi.data(); v.ovf_off = e->ovf_off.data(); v.ovf_idx = e->ovf_idx.data();
     v.n_tiles = e->n_groups; v.tile_cols = 32; v.win_base = e->win_base;
     v.ncols_all = all ? (int32_t)e->ncols_all : 0;
     v.ncols = (int32_t)(all ? std::max(e->ncols_cov, e->ncols_all) : e->ncols_cov);
