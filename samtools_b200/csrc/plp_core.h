@@ -29,21 +29,24 @@ namespace plp {
 // CIGAR ops, BAM encoding
 enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X };
 
-// 32-byte read descriptor built on the device by the read stage
+// 32-byte read descriptor built on the device by the read stage.  The first 16 bytes are all
+// a column needs for the common read shape ([S]<n>M[S], RD_SIMPLE); the second half is only
+// fetched for reads with indels / clips-with-pads / skips and for a few optional columns.
 struct alignas(16) ReadDesc {
     int32_t rpos;      // leftmost column, relative to the window base
     int32_t rend;      // one past the last column the read can appear in (== rpos: never)
-    uint64_t qoff;     // offset of qual[0]; nibble offset of the first base
-    uint32_t cig_off;  // first CIGAR op
-    int32_t l_qseq;
-    uint16_t n_cigar;
+    uint32_t qoff;     // offset of qual[0]; nibble offset of the first base
+    uint16_t qstart;   // RD_SIMPLE: query index aligned to rpos (qstart + span <= l_qseq is guaranteed)
     uint8_t mapq;
     uint8_t fl;        // RD_* bits
-    int32_t qstart;    // RD_SIMPLE: query index aligned to rpos
+    // ---- second half
+    uint32_t cig_off;  // first CIGAR op
+    int32_t l_qseq;
+    uint32_t n_cigar;
+    uint32_t pad_;
 };
 enum { RD_REV = 1, RD_SIMPLE = 2 };
 
-// one descriptor = two 16-byte words; on the device they go through the read-only path
 PLP_HD ReadDesc load_desc(const ReadDesc *p)
 {
 #if defined(__CUDA_ARCH__)
@@ -54,6 +57,43 @@ PLP_HD ReadDesc load_desc(const ReadDesc *p)
 #else
     return *p;
 #endif
+}
+// first half only (second half zero)
+PLP_HD ReadDesc load_hot(const ReadDesc *p)
+{
+#if defined(__CUDA_ARCH__)
+    union { uint4 w[2]; ReadDesc d; } u;
+    u.w[0] = __ldg(reinterpret_cast<const uint4 *>(p));
+    u.w[1] = make_uint4(0, 0, 0, 0);
+    return u.d;
+#else
+    ReadDesc d = *p; d.cig_off = 0; d.l_qseq = 0; d.n_cigar = 0; d.pad_ = 0;
+    return d;
+#endif
+}
+PLP_HD void load_cold(ReadDesc &d, const ReadDesc *p)
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 w = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+    d.cig_off = w.x; d.l_qseq = (int32_t)w.y; d.n_cigar = w.z;
+#else
+    d.cig_off = p->cig_off; d.l_qseq = p->l_qseq; d.n_cigar = p->n_cigar;
+#endif
+}
+
+// base character of the pileup sequence column: ".ACMGRSVTWYHKDBN" / ",acmgrsvtwyhkdbn"[code]
+// from packed immediates (no table load in the inner loop)
+PLP_HD char base_char(int code, bool rev)
+{
+    // bytes little-endian: index 0 is the lowest byte
+    const uint64_t fwd_lo = ((uint64_t)'.') | ((uint64_t)'A' << 8) | ((uint64_t)'C' << 16) | ((uint64_t)'M' << 24) | ((uint64_t)'G' << 32) |
+                            ((uint64_t)'R' << 40) | ((uint64_t)'S' << 48) | ((uint64_t)'V' << 56);
+    const uint64_t fwd_hi = ((uint64_t)'T') | ((uint64_t)'W' << 8) | ((uint64_t)'Y' << 16) | ((uint64_t)'H' << 24) | ((uint64_t)'K' << 32) |
+                            ((uint64_t)'D' << 40) | ((uint64_t)'B' << 48) | ((uint64_t)'N' << 56);
+    const uint64_t rev_lo = (fwd_lo | 0x2020202020202000ull) & ~0xffull | (uint64_t)',';
+    const uint64_t rev_hi = fwd_hi | 0x2020202020202020ull;
+    const uint64_t w = (code & 8) ? (rev ? rev_hi : fwd_hi) : (rev ? rev_lo : fwd_lo);
+    return (char)(w >> ((code & 7) * 8));
 }
 
 struct View {
@@ -135,9 +175,9 @@ PLP_HD int put_u64(char *p, uint64_t v)
     for (int i = n - 1; i >= 0; --i) { p[i] = (char)('0' + v % 10); v /= 10; }
     return n;
 }
-PLP_HD int base4(const uint8_t *seq4, uint64_t qoff, int32_t i)
+PLP_HD int base4(const uint8_t *seq4, uint32_t qoff, int32_t i)
 {
-    uint64_t n = qoff + (uint64_t)i;
+    const uint32_t n = qoff + (uint32_t)i;
     return (seq4[n >> 1] >> ((~n & 1) << 2)) & 0xf;
 }
 PLP_HD bool is_refop(int op) { return op == OP_M || op == OP_D || op == OP_N || op == OP_EQ || op == OP_X; }
@@ -199,7 +239,7 @@ constexpr int kCigarWalkMax = 8;
 PLP_HD void locate(const View &v, const ReadDesc &d, int32_t c, int &k, int32_t &x, int32_t &y, int &op, int &len)
 {
     const uint32_t *cg = v.cigar + d.cig_off;
-    const int n = d.n_cigar;
+    const int n = (int)d.n_cigar;
     if (n > kCigarWalkMax) {
         const int32_t *cx = v.cig_x + d.cig_off;
         int lo_ = 0, hi_ = n;
@@ -225,12 +265,12 @@ PLP_HD void resolve(const View &v, const ReadDesc &d, int32_t c, Ent &e)
     e.is_tail = (c == d.rend - 1);
     e.indel = 0; e.is_del = 0; e.is_refskip = 0;
     if (d.fl & RD_SIMPLE) {  // [H][S] M [S][H]
-        e.qpos = d.qstart + (c - d.rpos);
+        e.qpos = (int32_t)d.qstart + (c - d.rpos);
         e.k = -1;            // only needed for insertions, which a simple read has none of
         return;
     }
     const uint32_t *cg = v.cigar + d.cig_off;
-    const int n = d.n_cigar;
+    const int n = (int)d.n_cigar;
     int32_t x, y; int k, op, len;
     locate(v, d, c, k, x, y, op, len);
     e.k = k;
@@ -266,7 +306,7 @@ PLP_HD int ins_scan(const ReadDesc &d, const uint32_t *cg, int k, int &del_len)
 {
     int nb = 0;
     del_len = 0;
-    for (int j = k + 1; j < d.n_cigar; ++j) {
+    for (int j = k + 1; j < (int)d.n_cigar; ++j) {
         int op = cg[j] & 0xf, l = (int)(cg[j] >> 4);
         if (op == OP_P || op == OP_I) nb += l;
         else { if (op == OP_D) del_len = l; break; }
@@ -277,7 +317,7 @@ PLP_HD int ins_scan(const ReadDesc &d, const uint32_t *cg, int k, int &del_len)
 // base quality the reference tests against -Q ("qpos < l_qseq ? qual[qpos] : 0")
 PLP_HD int ent_qual(const View &v, const ReadDesc &d, const Ent &e)
 {
-    return e.qpos < d.l_qseq ? (int)v.qual[d.qoff + (uint64_t)e.qpos] : 0;
+    return e.qpos < d.l_qseq ? (int)v.qual[d.qoff + (uint32_t)e.qpos] : 0;
 }
 
 // ---- mpileup text for one (read, column) ------------------------------------
@@ -315,7 +355,7 @@ PLP_HD int mp_entry_write(const View &v, const MpConf &cf, const ReadDesc &d, co
             }
             if (ch == rb) ch = 0;
         }
-        *p++ = rev ? ",acmgrsvtwyhkdbn"[ch] : ".ACMGRSVTWYHKDBN"[ch];
+        *p++ = base_char(ch, rev);
     } else *p++ = e.is_refskip ? (rev ? '<' : '>') : ((rev && cf.rev_del) ? '#' : '*');
     int del_len = -e.indel;
     if (e.indel > 0) {
@@ -323,7 +363,7 @@ PLP_HD int mp_entry_write(const View &v, const MpConf &cf, const ReadDesc &d, co
         if (cf.no_ins < 2) { *p++ = '+'; p += put_u64(p, (uint64_t)len); }
         if (!cf.no_ins) {
             int j = 1;
-            for (int kk = e.k + 1; kk < d.n_cigar; ++kk) {
+            for (int kk = e.k + 1; kk < (int)d.n_cigar; ++kk) {
                 int op = cg[kk] & 0xf, l = (int)(cg[kk] >> 4);
                 if (op == OP_P) { for (int i = 0; i < l; ++i) *p++ = (rev && cf.rev_del) ? '#' : '*'; }
                 else if (op == OP_I) {
@@ -367,15 +407,16 @@ PLP_HD void mp_file_size(const View &v, const MpConf &cf, int f, int tile, int32
     const uint32_t ends = cf.no_ends ? 0u : 1u;
     for (int32_t t_ = 0; t_ < rr.n; ++t_) {
         const int32_t i = range_at(rr, t_);
-        const ReadDesc d = load_desc(v.desc + i);
+        ReadDesc d = load_hot(v.desc + i);
         const uint32_t rel = (uint32_t)(c - d.rpos);
         if (rel >= (uint32_t)(d.rend - d.rpos)) continue;
         ++s.nplp;
+        if (!(d.fl & RD_SIMPLE) || cf.out_qpos5) load_cold(d, v.desc + i);
         if (d.fl & RD_SIMPLE) {
             // the common case ([S]<n>M[S]): one base, no indel text; 2 extra bytes at the read's
             // first column ("^" + mapq), 1 at its last ("$")
-            const int32_t qpos = d.qstart + (int32_t)rel;
-            const int q = qpos < d.l_qseq ? (int)v.qual[d.qoff + (uint64_t)qpos] : 0;
+            const int32_t qpos = (int32_t)d.qstart + (int32_t)rel;
+            const int q = (int)v.qual[d.qoff + (uint32_t)qpos];
             if (q < cf.min_baseQ) continue;
             ++s.cnt;
             s.seq_len += 1u + (ends & (uint32_t)(rel == 0)) * 2u + (ends & (uint32_t)(c == d.rend - 1));
@@ -452,20 +493,20 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
         }
         for (int32_t t_ = 0; t_ < rr.n; ++t_) {
         const int32_t i = range_at(rr, t_);
-            const ReadDesc d = load_desc(v.desc + i);
+            ReadDesc d = load_hot(v.desc + i);
             const uint32_t rel = (uint32_t)(c - d.rpos);
             if (rel >= (uint32_t)(d.rend - d.rpos)) continue;
+            if (!(d.fl & RD_SIMPLE) || cf.out_qpos5) load_cold(d, v.desc + i);
             int q, qpos1; int32_t q5;
             if (d.fl & RD_SIMPLE) {
-                const int32_t qpos = d.qstart + (int32_t)rel;
-                const bool in = qpos < d.l_qseq;
-                q = in ? (int)v.qual[d.qoff + (uint64_t)qpos] : 0;
+                const int32_t qpos = (int32_t)d.qstart + (int32_t)rel;
+                q = (int)v.qual[d.qoff + (uint32_t)qpos];
                 if (q < cf.min_baseQ) continue;
                 const bool rev = d.fl & RD_REV;
                 if (!cf.no_ends && rel == 0) { *ps++ = '^'; *ps++ = (char)(d.mapq > 93 ? 126 : d.mapq + 33); }
-                int ch = in ? base4(v.seq4, d.qoff, qpos) : 15;
+                int ch = base4(v.seq4, d.qoff, qpos);
                 if (ch == rb) ch = 0;
-                *ps++ = rev ? ",acmgrsvtwyhkdbn"[ch] : ".ACMGRSVTWYHKDBN"[ch];
+                *ps++ = base_char(ch, rev);
                 if (!cf.no_ends && c == d.rend - 1) *ps++ = '$';
                 qpos1 = qpos + 1; q5 = rev ? d.l_qseq - qpos : qpos + 1;
             } else {
@@ -543,25 +584,26 @@ PLP_HD void dp_file_column(const View &v, const DpConf &cf, int f, int tile, int
     const ReadRange rr = read_range(v, f, tile);
     for (int32_t t_ = 0; t_ < rr.n; ++t_) {
         const int32_t i = range_at(rr, t_);
-        const ReadDesc d = load_desc(v.desc + i);
-        if (c < d.rpos || c >= d.rend) continue;
+        ReadDesc d = load_hot(v.desc + i);
+        if ((uint32_t)(c - d.rpos) >= (uint32_t)(d.rend - d.rpos)) continue;
         o.spanned = true;
+        if (!(d.fl & RD_SIMPLE)) load_cold(d, v.desc + i);
         const int32_t clip = v.clip ? v.clip[i] : INT32_MIN;
         if (d.fl & RD_SIMPLE) {
             if (c < clip) continue;
-            int q = d.qstart + (c - d.rpos);
-            if (!cf.min_qual || v.qual[d.qoff + (uint64_t)q] >= cf.min_qual) ++o.depth;
+            int q = (int)d.qstart + (c - d.rpos);
+            if (!cf.min_qual || v.qual[d.qoff + (uint32_t)q] >= cf.min_qual) ++o.depth;
             continue;
         }
         int32_t x, y; int k, op, len;
         locate(v, d, c, k, x, y, op, len);
-        if (k >= d.n_cigar || c < clip) continue;
+        if (k >= (int)d.n_cigar || c < clip) continue;
         if (is_mop(op)) {
             int q = y + (c - x);
-            if (!cf.min_qual || v.qual[d.qoff + (uint64_t)q] >= cf.min_qual) ++o.depth;
+            if (!cf.min_qual || v.qual[d.qoff + (uint32_t)q] >= cf.min_qual) ++o.depth;
         } else if (op == OP_D && cf.count_del) {
             // -J: a deletion column borrows the quality of the next query base (bam2depth.c:418-423)
-            if (y < d.l_qseq) { if (v.qual[d.qoff + (uint64_t)y] >= cf.min_qual) ++o.depth; }
+            if (y < d.l_qseq) { if (v.qual[d.qoff + (uint32_t)y] >= cf.min_qual) ++o.depth; }
             else ++o.depth;
         }
     }
@@ -578,14 +620,21 @@ PLP_HD void cv_column(const View &v, int32_t min_baseQ, int tile, int32_t c, CvC
         int32_t dpos = 0;
         for (int32_t t_ = 0; t_ < rr.n; ++t_) {
         const int32_t i = range_at(rr, t_);
-            const ReadDesc d = load_desc(v.desc + i);
-            if (c < d.rpos || c >= d.rend) continue;
+            ReadDesc d = load_hot(v.desc + i);
+            if ((uint32_t)(c - d.rpos) >= (uint32_t)(d.rend - d.rpos)) continue;
+            ++dpos;
+            if (d.fl & RD_SIMPLE) {
+                const int q = v.qual[d.qoff + (uint32_t)d.qstart + (uint32_t)(c - d.rpos)];
+                if (q < min_baseQ) --dpos;
+                else { o.sum_bq += (uint64_t)q; ++o.qbases; }
+                continue;
+            }
+            load_cold(d, v.desc + i);
             Ent e;
             resolve(v, d, c, e);
-            ++dpos;
             if (e.is_del || e.is_refskip) --dpos;
             else if (e.qpos < d.l_qseq) {
-                int q = v.qual[d.qoff + (uint64_t)e.qpos];
+                int q = v.qual[d.qoff + (uint32_t)e.qpos];
                 if (q < min_baseQ) --dpos;
                 else { o.sum_bq += (uint64_t)q; ++o.qbases; }
             } else ++o.missing;

@@ -174,10 +174,10 @@ PLP_HD void stage_build_desc(const RawSoA &r, const b200_stage_conf_t &cf, int64
     int32_t span = rl;
     if (cf.mode == B200_MODE_DEPTH) span = ((r.flag[i] & 4) || n == 0 || rl == 0) ? 1 : rl;   // bam_endpos
     d.rend = keep ? d.rpos + span : d.rpos;
-    d.qoff = r.qual_off[i];
+    d.qoff = (uint32_t)r.qual_off[i];
     d.cig_off = (uint32_t)r.cigar_off[i];
     d.l_qseq = r.l_qseq[i];
-    d.n_cigar = (uint16_t)n;
+    d.n_cigar = (uint32_t)n; d.pad_ = 0;
     d.mapq = r.mapq[i];
     d.fl = (r.flag[i] & 16) ? RD_REV : 0;
     d.qstart = 0;
@@ -190,7 +190,7 @@ PLP_HD void stage_build_desc(const RawSoA &r, const b200_stage_conf_t &cf, int64
             ++k;
             if (k < n && (cg[k] & 0xf) == OP_S) ++k;
             while (k < n && (cg[k] & 0xf) == OP_H) ++k;
-            if (k == n) { d.fl |= RD_SIMPLE; d.qstart = qs; }
+            if (k == n && qs <= 65535 && qs + rl <= r.l_qseq[i]) { d.fl |= RD_SIMPLE; d.qstart = (uint16_t)qs; }
         }
     }
     if (n > kCigarWalkMax) {   // per-op prefix arrays for long CIGARs (see plp_core.h locate())
