@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(TILE) k_mpileup_write(MpFmt fmt, const uint32_
     text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
 }
 
+#include "mpileup_rm.cuh"
+
 // depth rows "name\tpos(\tdepth)*\n" (bam2depth.c:234-244)
 struct DpFmt {
     View v; DpConf cf;
@@ -593,6 +595,11 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
     s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
+    s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major kernels, 1: column-major kernels
+    if (e->chained) e->variant = 1;
+    e->smem_text_rm = 36 * 1024;
+    s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text_rm = (uint32_t)atoi(s);
+    cudaFuncSetAttribute(k_mp_rm_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text_rm + 16);
     cudaFuncSetAttribute(k_mpileup_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_depth_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_mpileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
@@ -901,7 +908,39 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     fmt.cf.out_qpos5 = c->out_qpos5; fmt.cf.n_star_cols = c->n_star_cols;
     const int per = 2 + (c->out_mapq ? 1 : 0) + (c->out_qpos ? 12 : 0) + (c->out_qpos5 ? 13 : 0);
     const uint64_t bound = e->text_bound(per, 1 + 2 * (3 + c->n_star_cols)) ;
-    return run_text(e, k_mpileup, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
+    if (e->variant != 0) return run_text(e, k_mpileup, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
+    // ---- read-major kernels (default)
+    const int32_t ncols = fmt.v.ncols;
+    const int nt = (ncols + RM_COLS - 1) / RM_COLS;
+    *out_len = 0; e->last_kernel_ms = 0;
+    if (nt == 0) return 0;
+    ENSURE(out, (size_t)bound + 64);
+    ENSURE(col_n, (size_t)ncols + 1);
+    ENSURE(col_state, ((size_t)ncols * (size_t)e->n_files * sizeof(MpFileSz) + 7) / 8 + 1);
+    ENSURE(tile_total, (size_t)nt + 1); ENSURE(col_off, (size_t)nt + 2);
+    const int nb = nblk(nt, 256);
+    ENSURE(status, (size_t)nb + 1);
+    CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
+    CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    k_mp_rm_size<<<nt, RM_WARPS * 32, 0, e->stream>>>(fmt.v, fmt.cf, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
+    k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
+    k_mp_rm_write<<<nt, RM_WARPS * 32, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
+                                                                         e->smem_text_rm, e->use_tma); e->launches++;
+    CK(cudaEventRecord(e->ev1, e->stream));
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, e->col_off + nt, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
+    if (total > bound) { snprintf(e->err, sizeof e->err, "internal: output %llu exceeds bound %llu", total, (unsigned long long)bound); return -1; }
+    *out_len = (size_t)total; e->last_out_len = (size_t)total;
+    if (out) {
+        if (total > out_cap) { snprintf(e->err, sizeof e->err, "output buffer too small: need %llu bytes", total); return -2; }
+        CK(cudaMemcpyAsync(out, e->out, (size_t)total, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return 0;
 }
 
 extern "C" int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, char *out, size_t out_cap, size_t *out_len)

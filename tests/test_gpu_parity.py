@@ -139,6 +139,7 @@ def test_c2_size_properties():
     soa = noref(synth.make_batch(length=1_000_000, depth=30, seed=2))
     digests = {}
     for tag, env in (('tma', {'B200_PLP_TMA': '1'}), ('vec', {'B200_PLP_TMA': '0'}), ('direct', {'B200_PLP_SMEM_TEXT': '1024'}),
+                     ('colmajor', {'B200_PLP_VARIANT': '1'}), ('colmajor_direct', {'B200_PLP_VARIANT': '1', 'B200_PLP_SMEM_TEXT': '1024'}),
                      ('chained', {'B200_PLP_CHAINED': '1'}), ('chained_direct', {'B200_PLP_CHAINED': '1', 'B200_PLP_SMEM_TEXT': '1024'})):
         os.environ.update(env)
         e = engine.Engine(0)
@@ -156,4 +157,4 @@ def test_c2_size_properties():
             # depth column sums to the number of kept (read, column) pairs that pass -Q13; positions ascend
             pos = np.array([int(l.split(b'\t', 2)[1]) for l in lines[:-1:997]])
             assert (np.diff(pos) > 0).all()
-    assert len(set(digests.values())) == 1, digests   # two-launch / chained single-launch, TMA / vector / direct-to-HBM stores all agree
+    assert len(set(digests.values())) == 1, digests   # read-major / column-major / chained single-launch kernels, TMA / vector / direct-to-HBM stores all agree
