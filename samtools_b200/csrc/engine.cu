@@ -595,7 +595,7 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
     s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
-    s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major kernels, 1: column-major kernels
+    s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + column-major write (default), 1: column-major both, 2: read-major both
     if (e->chained) e->variant = 1;
     e->smem_text_rm = 36 * 1024;
     s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text_rm = (uint32_t)atoi(s);
@@ -908,25 +908,33 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     fmt.cf.out_qpos5 = c->out_qpos5; fmt.cf.n_star_cols = c->n_star_cols;
     const int per = 2 + (c->out_mapq ? 1 : 0) + (c->out_qpos ? 12 : 0) + (c->out_qpos5 ? 13 : 0);
     const uint64_t bound = e->text_bound(per, 1 + 2 * (3 + c->n_star_cols)) ;
-    if (e->variant != 0) return run_text(e, k_mpileup, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
-    // ---- read-major kernels (default)
+    if (e->variant == 1) return run_text(e, k_mpileup, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
+    // ---- default: read-major sizing (coalesced along the reads), then a write kernel:
+    //      variant 0 = column-major write (thread per position), variant 2 = read-major write
     const int32_t ncols = fmt.v.ncols;
-    const int nt = (ncols + RM_COLS - 1) / RM_COLS;
+    const int ntr = (ncols + RM_COLS - 1) / RM_COLS;     // read-major CTAs (256 columns)
+    const int nt = ntr * 2;                              // 128-column tiles of the offset scan
     *out_len = 0; e->last_kernel_ms = 0;
-    if (nt == 0) return 0;
+    if (ntr == 0) return 0;
     ENSURE(out, (size_t)bound + 64);
-    ENSURE(col_n, (size_t)ncols + 1);
-    ENSURE(col_state, ((size_t)ncols * (size_t)e->n_files * sizeof(MpFileSz) + 7) / 8 + 1);
+    ENSURE(col_n, (size_t)nt * TILE + 1);
+    ENSURE(col_state, ((size_t)nt * TILE * (size_t)e->n_files * sizeof(MpFileSz) + 7) / 8 + 1);
     ENSURE(tile_total, (size_t)nt + 1); ENSURE(col_off, (size_t)nt + 2);
     const int nb = nblk(nt, 256);
     ENSURE(status, (size_t)nb + 1);
     CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
     CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
-    k_mp_rm_size<<<nt, RM_WARPS * 32, 0, e->stream>>>(fmt.v, fmt.cf, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
+    k_mp_rm_size<<<ntr, RM_WARPS * 32, 0, e->stream>>>(fmt.v, fmt.cf, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
     k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
-    k_mp_rm_write<<<nt, RM_WARPS * 32, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
-                                                                         e->smem_text_rm, e->use_tma); e->launches++;
+    if (e->variant == 2) {
+        k_mp_rm_write<<<ntr, RM_WARPS * 32, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
+                                                                              e->smem_text_rm, e->use_tma);
+    } else {
+        const int ntw = (ncols + TILE - 1) / TILE;
+        k_mpileup_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+    }
+    e->launches++;
     CK(cudaEventRecord(e->ev1, e->stream));
     unsigned long long total = 0;
     CK(cudaMemcpyAsync(&total, e->col_off + nt, 8, cudaMemcpyDeviceToHost, e->stream));

@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(RM_WARPS * 32) k_mp_rm_size(View v, MpConf cf,
     for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
     if (lane == 0) s_ws[w] = tot;
     __syncthreads();
-    if (threadIdx.x == 0) { uint32_t t = 0; for (int k = 0; k < RM_WARPS; ++k) t += s_ws[k]; tile_total[blockIdx.x] = t; }
+    // totals per 128 columns (the granularity of the tile-offset scan, shared with the column-major write kernel)
+    if (threadIdx.x < 2) tile_total[blockIdx.x * 2 + threadIdx.x] = s_ws[2 * threadIdx.x] + s_ws[2 * threadIdx.x + 1];
 }
 
 struct RmWriteSm {   // per-column layout of the current file section (offsets into the tile text)
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(RM_WARPS * 32) k_mp_rm_write(View v, MpConf cf
     uint32_t wbase = 0, total = 0;
     for (int k = 0; k < RM_WARPS; ++k) { if (k < w) wbase += s_ws[k]; total += s_ws[k]; }
     if (total == 0) return;
-    const uint64_t base = tile_base[blockIdx.x];
+    const uint64_t base = tile_base[blockIdx.x * 2];
     const uint32_t phase = (uint32_t)(base & 15);
     const bool in_smem = total + phase <= smem_cap;
     char *text = in_smem ? s_text + phase : out + base;     // very deep tiles format straight into HBM

@@ -491,38 +491,55 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
             rb = 15;
             if ((int64_t)c < v.ref_len_rel) { const int64_t ri = (int64_t)c - v.ref_off; if (ri >= 0 && ri < v.ref_n) rb = nt16_of((unsigned char)v.ref[ri]); }
         }
-        for (int32_t t_ = 0; t_ < rr.n; ++t_) {
-        const int32_t i = range_at(rr, t_);
-            ReadDesc d = load_hot(v.desc + i);
+        const bool ends = !cf.no_ends, extras = (cf.out_mapq | cf.out_qpos | cf.out_qpos5) != 0;
+        const int minq = cf.min_baseQ;
+        auto body = [&](ReadDesc d, int32_t i) {
             const uint32_t rel = (uint32_t)(c - d.rpos);
-            if (rel >= (uint32_t)(d.rend - d.rpos)) continue;
-            if (!(d.fl & RD_SIMPLE) || cf.out_qpos5) load_cold(d, v.desc + i);
-            int q, qpos1; int32_t q5;
+            if (rel >= (uint32_t)(d.rend - d.rpos)) return;
+            int q, qpos1 = 0; int32_t q5 = 0;
             if (d.fl & RD_SIMPLE) {
-                const int32_t qpos = (int32_t)d.qstart + (int32_t)rel;
-                q = (int)v.qual[d.qoff + (uint32_t)qpos];
-                if (q < cf.min_baseQ) continue;
+                const uint32_t qi = d.qoff + (uint32_t)d.qstart + rel;
+                q = (int)v.qual[qi];
+                const uint8_t sb = v.seq4[qi >> 1];          // issued together with the quality load
+                if (q < minq) return;
                 const bool rev = d.fl & RD_REV;
-                if (!cf.no_ends && rel == 0) { *ps++ = '^'; *ps++ = (char)(d.mapq > 93 ? 126 : d.mapq + 33); }
-                int ch = base4(v.seq4, d.qoff, qpos);
+                if (ends && rel == 0) { *ps++ = '^'; *ps++ = (char)(d.mapq > 93 ? 126 : d.mapq + 33); }
+                int ch = (sb >> ((~qi & 1) << 2)) & 0xf;
                 if (ch == rb) ch = 0;
                 *ps++ = base_char(ch, rev);
-                if (!cf.no_ends && c == d.rend - 1) *ps++ = '$';
-                qpos1 = qpos + 1; q5 = rev ? d.l_qseq - qpos : qpos + 1;
+                if (ends && c == d.rend - 1) *ps++ = '$';
+                if (extras) {
+                    const int32_t qpos = (int32_t)d.qstart + (int32_t)rel;
+                    qpos1 = qpos + 1;
+                    if (cf.out_qpos5) { load_cold(d, v.desc + i); q5 = rev ? d.l_qseq - qpos : qpos + 1; }
+                }
             } else {
+                load_cold(d, v.desc + i);
                 const uint32_t *cg = v.cigar + d.cig_off;
                 Ent e;
                 resolve(v, d, c, e);
                 q = ent_qual(v, d, e);
-                if (q < cf.min_baseQ) continue;
+                if (q < minq) return;
                 ps += mp_entry_write(v, cf, d, cg, e, c, ps);
                 qpos1 = e.qpos + 1; q5 = qpos5_of(d, e);
             }
             *pq++ = (char)(q + 33 < 126 ? q + 33 : 126);
-            if (cf.out_mapq) { int m = d.mapq + 33; *pm++ = (char)(m > 126 ? 126 : m); }
-            if (cf.out_qpos) { if (n) *pb++ = ','; pb += put_i32(pb, qpos1); }
-            if (cf.out_qpos5) { if (n) *pb5++ = ','; pb5 += put_i32(pb5, q5); }
-            ++n;
+            if (extras) {
+                if (cf.out_mapq) { int m = d.mapq + 33; *pm++ = (char)(m > 126 ? 126 : m); }
+                if (cf.out_qpos) { if (n) *pb++ = ','; pb += put_i32(pb, qpos1); }
+                if (cf.out_qpos5) { if (n) *pb5++ = ','; pb5 += put_i32(pb5, q5); }
+                ++n;
+            }
+        };
+        for (int32_t t_ = 0; t_ < rr.n_ovf; ++t_) { const int32_t i = rr.ovf[t_]; body(load_hot(v.desc + i), i); }
+        const int32_t hi_ = rr.lo + (rr.n - rr.n_ovf);
+        if (rr.lo < hi_) {
+            ReadDesc dn = load_hot(v.desc + rr.lo);             // software pipelining: fetch descriptor i+1 while i is formatted
+            for (int32_t i = rr.lo; i < hi_; ++i) {
+                const ReadDesc d = dn;
+                if (i + 1 < hi_) dn = load_hot(v.desc + i + 1);
+                body(d, i);
+            }
         }
     }
     pq = p + (s.seq_len ? s.seq_len : 1);
