@@ -18,7 +18,7 @@
 //
 // Mapping: one warp per read.  Lanes own the cells of the band (2*bw+1 = 15 by
 // default) for the parallel M/I terms; the sequential D chain and the ordered
-// row sums run as a lane-uniform loop fed by shuffles.  The forward matrix
+// row sums run as a lane-uniform loop over a per-warp shared-memory copy of the row.  The forward matrix
 // lives in an HBM slab per resident warp (L2-resident); backward keeps two rows.
 #pragma once
 
@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
                                              unsigned long long slab_doubles, const double *q2p, const double *qthr,
                                              unsigned long long *work)
 {
+    // per-warp exchange rows: the ordered (sequential-in-k) parts read the band cells of the row from
+    // shared memory (broadcast loads that pipeline) instead of one shuffle round trip per cell
+    __shared__ double s_x[4][2][32];
+    double (*sx)[32] = s_x[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double *slab = slabs + (size_t)gw * slab_doubles;
@@ -132,7 +136,9 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
                 double M = 0., I = 0.;
                 if (act) { M = emis(ref_code(r, pl.xb + k - 1), qc, ql) * bM; I = BAQ_EI * bI; }
                 const int cnt = min(32, end - kb + 1);
-                for (int j = 0; j < cnt; ++j) sum += shfl_d(M, j) + shfl_d(I, j);
+                sx[0][lane] = M; sx[1][lane] = I; __syncwarp();
+                for (int j = 0; j < cnt; ++j) sum += sx[0][j] + sx[1][j];
+                __syncwarp();
                 if (act) { const int u = (k + 1) * 3; fi[u] = M; fi[u + 1] = I; fi[u + 2] = 0.; }
             }
             __syncwarp();
@@ -166,13 +172,15 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
                 }
                 const int cnt = min(32, end - kb + 1);
                 double myD = 0.;
+                sx[0][lane] = M; sx[1][lane] = I; __syncwarp();
                 for (int j = 0; j < cnt; ++j) {
-                    const double Mj = shfl_d(M, j), Ij = shfl_d(I, j);
+                    const double Mj = sx[0][j], Ij = sx[1][j];
                     const double Dj = tc + m[8] * Dc;
                     sum += Mj + Ij + Dj;
                     if (lane == j) myD = Dj;
                     tc = m[2] * Mj; Dc = Dj;
                 }
+                __syncwarp();
                 if (act) { const int u = (k - x + 1) * 3; fi[u] = M; fi[u + 1] = I; fi[u + 2] = myD; }
             }
             __syncwarp();
@@ -198,7 +206,9 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
                 double t = 0.;
                 if (k <= endl) { const int u = (k - xl + 1) * 3; t = fl[u] * sM + fl[u + 1] * sI; }
                 const int cnt = min(32, endl - kb + 1);
-                for (int j = 0; j < cnt; ++j) sum += shfl_d(t, j);
+                sx[0][lane] = t; __syncwarp();
+                for (int j = 0; j < cnt; ++j) sum += sx[0][j];
+                __syncwarp();
             }
             s_last = sum;
             if (lane == 0) S[lq + 1] = sum;
@@ -242,12 +252,14 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
                     }
                     const int cnt = min(32, kt - bbeg + 1);
                     double myD = 0., myDn = 0.;
+                    sx[0][lane] = e; __syncwarp();
                     for (int j = 0; j < cnt; ++j) {
-                        const double ej = shfl_d(e, j);
+                        const double ej = sx[0][j];
                         const double Dj = (ej * m[6] + m[8] * Dn) * y;
                         if (lane == j) { myD = Dj; myDn = Dn; }
                         Dn = Dj;
                     }
+                    __syncwarp();
                     if (act) { const int u = (k - x + 1) * 3; bcur[u] = p0 + m[2] * myDn; bcur[u + 1] = p1; bcur[u + 2] = myD; }
                 }
                 __syncwarp();
@@ -276,13 +288,15 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
                         z0 = f0 * b0; z1 = f1v * b1;
                     }
                     const int cnt = min(32, mend - kb + 1);
+                    sx[0][lane] = z0; sx[1][lane] = z1; __syncwarp();
                     for (int j = 0; j < cnt; ++j) {
-                        const double a = shfl_d(z0, j), b = shfl_d(z1, j);
+                        const double a = sx[0][j], b = sx[1][j];
                         if (a > mx) { mx = a; max_k = (kb + j - 1) << 2 | 0; }
                         sum += a;
                         if (b > mx) { mx = b; max_k = (kb + j - 1) << 2 | 1; }
                         sum += b;
                     }
+                    __syncwarp();
                 }
                 if (lane == 0) {
                     mx /= sum;
@@ -377,8 +391,8 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
     if (n_idx == 0) return 0;
     const unsigned long long slab = h[1] + 2 * h[2] / 8 + 8;   // + left/right byte rows
     // resident warps: 4 per block, up to 16 blocks/SM, bounded by ~2 GB of slabs and by the work
-    int64_t warps = (int64_t)e->n_sm * 16 * 4;
-    const int64_t cap = (int64_t)((2ULL << 30) / (slab * 8));
+    int64_t warps = (int64_t)e->n_sm * 12 * 4;   // 48 warps per SM (register-limited), each latency-bound: occupancy is the lever
+    const int64_t cap = (int64_t)((6ULL << 30) / (slab * 8));
     if (warps > cap) warps = cap;
     if (warps > n_idx) warps = n_idx;
     if (warps < 1) warps = 1;
