@@ -9,6 +9,7 @@ int main_mpileup(int argc, char **argv, int gl);
 int main_depth(int argc, char **argv);
 int main_coverage(int argc, char **argv);
 int main_view(int argc, char **argv);
+int main_pileup_dump(int argc, char **argv);
 int main(int argc, char **argv)
 {
     if (argc < 2) { fprintf(stderr, "usage: plp_oracle mpileup|depth|coverage|gl [options]\n"); return 1; }
@@ -17,6 +18,7 @@ int main(int argc, char **argv)
     if (!strcmp(argv[1], "depth")) return main_depth(argc - 1, argv + 1);
     if (!strcmp(argv[1], "coverage")) return main_coverage(argc - 1, argv + 1);
     if (!strcmp(argv[1], "view")) return main_view(argc - 1, argv + 1);
+    if (!strcmp(argv[1], "pileup-dump")) return main_pileup_dump(argc - 1, argv + 1);
     fprintf(stderr, "plp_oracle: unknown command '%s'\n", argv[1]);
     return 1;
 }

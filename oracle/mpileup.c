@@ -491,3 +491,39 @@ int main_mpileup(int argc, char **argv, int gl)
     } else ret = mpileup(&c, argc - optind, argv + optind);
     return ret;
 }
+
+/* `pileup-dump [-o] [-d maxcnt] files...`: every pile1_t field per column, for checking the
+ * htslib-compatible iterator tier of the product (tests/compat/plp_dump.cpp) */
+static int dump_pull(void *data, rec_t *b) { return reader_next((reader_t *)data, b); }
+int main_pileup_dump(int argc, char **argv)
+{
+    int overlaps = 0, maxcnt = 8000, a = 1, i, j;
+    for (; a < argc && argv[a][0] == '-'; ++a) {
+        if (!strcmp(argv[a], "-o")) overlaps = 1;
+        else if (!strcmp(argv[a], "-d") && a + 1 < argc) maxcnt = atoi(argv[++a]);
+    }
+    int n = argc - a;
+    if (n < 1) return 1;
+    void **data = calloc((size_t)n, sizeof(void *));
+    for (i = 0; i < n; i++) { data[i] = reader_open(argv[a + i], NULL); if (!data[i]) return 1; }
+    mplp_t *it = mplp_init(n, dump_pull, data);
+    if (overlaps) mplp_init_overlaps(it);
+    mplp_set_maxcnt(it, maxcnt);
+    int *n_plp = calloc((size_t)n, sizeof(int)); const pile1_t **plp = calloc((size_t)n, sizeof(pile1_t *));
+    int tid, ret; hpos_t pos; str_t ins = {0, 0, NULL};
+    while ((ret = mplp_auto(it, &tid, &pos, n_plp, plp)) > 0) {
+        printf("%d\t%lld", tid, (long long)pos);
+        for (i = 0; i < n; i++) {
+            printf("\t%d:", n_plp[i]);
+            for (j = 0; j < n_plp[i]; j++) {
+                const pile1_t *p = plp[i] + j;
+                int q = p->qpos < p->b->l_qseq ? p->b->qual[p->qpos] : -1, dl = 0;
+                int il = plp_insertion(p, &ins, &dl);
+                printf(" %s/%d/%d/%d%d%d%d/%d/%d/%s/%d", p->b->qname, p->qpos, p->indel, p->is_del, p->is_head, p->is_tail, p->is_refskip,
+                       p->cigar_ind, q, il > 0 ? ins.s : "-", dl);
+            }
+        }
+        putchar('\n');
+    }
+    return ret < 0 ? 1 : 0;
+}

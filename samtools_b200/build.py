@@ -34,10 +34,12 @@ def _sources(d, exts):
 
 def build_engine(force=False, verbose=False):
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
-    srcs = _sources(CSRC, ('.cu', '.cuh', '.h')) + [os.path.join(ROOT, 'include', 'b200_pileup.h')]
+    srcs = _sources(CSRC, ('.cu', '.cuh', '.h')) + [os.path.join(ROOT, 'include', 'b200_pileup.h'), os.path.join(ROOT, 'include', 'b200_htslib_compat.h'),
+                                                    os.path.join(CSRC, 'host', 'plp_compat.cpp')]
     if force or _newer(LIB, srcs):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, os.path.join(CSRC, 'engine.cu')]
+        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, os.path.join(CSRC, 'engine.cu'),
+                                                                                os.path.join(CSRC, 'host', 'plp_compat.cpp')]
         subprocess.run(cmd, check=True)
     return LIB
 
@@ -53,6 +55,18 @@ def build_cli(force=False):
     return BIN
 
 
+def build_compat_client(force=False):
+    """tests/compat/plp_dump: a client of the htslib-compatible iterator tier (include/b200_htslib_compat.h)."""
+    src = os.path.join(ROOT, 'tests', 'compat', 'plp_dump.cpp')
+    exe = os.path.join(ROOT, 'tests', 'compat', '_build', 'plp_dump')
+    if force or _newer(exe, [src, LIB, os.path.join(ROOT, 'include', 'b200_htslib_compat.h')]):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.run(['g++', '-std=c++17', '-O2', '-g', '-Wall', '-I', os.path.join(ROOT, 'include'), '-o', exe, src,
+                        os.path.join(CSRC, 'host', 'hts_io.cpp'), '-L' + os.path.dirname(LIB), '-lb200pileup',
+                        '-Wl,-rpath,$ORIGIN/../../../samtools_b200/lib', '-lz'], check=True)
+    return exe
+
+
 def build_oracle():
     subprocess.run(['make', '-s', '-C', os.path.join(ROOT, 'oracle')], check=True)
     return os.path.join(ROOT, 'oracle', '_build', 'plp_oracle')
@@ -61,6 +75,7 @@ def build_oracle():
 def build_all(force=False, verbose=False):
     build_engine(force, verbose)
     build_cli(force)
+    build_compat_client(force)
     build_oracle()
 
 

@@ -1,0 +1,69 @@
+// plp_dump.cpp -- test client of the htslib-compatible iterator tier (include/b200_htslib_compat.h).
+// Written the way an htslib user writes a pileup loop (cf. coverage.c:572-589): a pull callback
+// fills bam1_t records, bam_mplp64_auto() hands out columns.  Prints every bam_pileup1_t field so the
+// test can diff it against the CPU oracle's iterator (`plp_oracle pileup-dump`).
+#include "b200_htslib_compat.h"
+#include "../../samtools_b200/csrc/host/hts_io.hpp"
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+
+struct Src { std::unique_ptr<b200::AlnReader> rd; };
+
+static int pull(void *data, bam1_t *b)
+{
+    Src *s = (Src *)data;
+    b200::Record r;
+    int ret = s->rd->next(r);
+    if (ret < 0) return ret;
+    const size_t lq = r.qname.size() + 1, l_qname = (lq + 3) & ~(size_t)3;
+    const size_t need = l_qname + 4 * r.cigar.size() + r.seq4.size() + r.qual.size() + r.aux.size();
+    if (b->m_data < need) { b->data = (uint8_t *)realloc(b->data, need); b->m_data = (uint32_t)need; }
+    memset(b->data, 0, l_qname);
+    memcpy(b->data, r.qname.c_str(), lq);
+    uint8_t *p = b->data + l_qname;
+    memcpy(p, r.cigar.data(), 4 * r.cigar.size()); p += 4 * r.cigar.size();
+    memcpy(p, r.seq4.data(), r.seq4.size()); p += r.seq4.size();
+    memcpy(p, r.qual.data(), r.qual.size()); p += r.qual.size();
+    memcpy(p, r.aux.data(), r.aux.size());
+    b->l_data = (int)need;
+    b->core.pos = r.pos; b->core.tid = r.tid; b->core.qual = r.mapq; b->core.flag = r.flag; b->core.l_qname = (uint16_t)l_qname;
+    b->core.l_extranul = (uint8_t)(l_qname - lq); b->core.n_cigar = (uint32_t)r.cigar.size(); b->core.l_qseq = r.l_qseq;
+    b->core.mtid = r.mtid; b->core.mpos = r.mpos; b->core.isize = r.isize;
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    bool overlaps = false; int maxcnt = 8000; int a = 1;
+    for (; a < argc && argv[a][0] == '-'; ++a) {
+        if (!strcmp(argv[a], "-o")) overlaps = true;
+        else if (!strcmp(argv[a], "-d") && a + 1 < argc) maxcnt = atoi(argv[++a]);
+    }
+    const int n = argc - a;
+    if (n < 1) { fprintf(stderr, "usage: plp_dump [-o] [-d maxcnt] in.sam [in2.sam ...]\n"); return 1; }
+    std::vector<Src> src((size_t)n); std::vector<void *> data;
+    for (int i = 0; i < n; ++i) { src[(size_t)i].rd = b200::AlnReader::open(argv[a + i]); if (!src[(size_t)i].rd) return 1; data.push_back(&src[(size_t)i]); }
+    bam_mplp_t it = bam_mplp_init(n, pull, data.data());
+    if (!it) { fprintf(stderr, "plp_dump: no CUDA pileup engine\n"); return 1; }
+    if (overlaps) bam_mplp_init_overlaps(it);
+    bam_mplp_set_maxcnt(it, maxcnt);
+    std::vector<int> n_plp((size_t)n); std::vector<const bam_pileup1_t *> plp((size_t)n);
+    int tid, ret; hts_pos_t pos; char ins[4096];
+    while ((ret = bam_mplp64_auto(it, &tid, &pos, n_plp.data(), plp.data())) > 0) {
+        printf("%d\t%lld", tid, (long long)pos);
+        for (int i = 0; i < n; ++i) {
+            printf("\t%d:", n_plp[(size_t)i]);
+            for (int j = 0; j < n_plp[(size_t)i]; ++j) {
+                const bam_pileup1_t *p = plp[(size_t)i] + j;
+                int q = p->qpos < p->b->core.l_qseq ? bam_get_qual(p->b)[p->qpos] : -1, dl = 0;
+                int il = b200_plp_insertion(p, ins, sizeof ins, &dl);
+                printf(" %s/%d/%d/%d%d%d%d/%d/%d/%s/%d", bam_get_qname(p->b), p->qpos, p->indel, p->is_del, p->is_head, p->is_tail, p->is_refskip,
+                       p->cigar_ind, q, il > 0 ? ins : "-", dl);
+            }
+        }
+        putchar('\n');
+    }
+    bam_mplp_destroy(it);
+    return ret < 0 ? 1 : 0;
+}

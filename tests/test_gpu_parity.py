@@ -158,3 +158,25 @@ def test_c2_size_properties():
             pos = np.array([int(l.split(b'\t', 2)[1]) for l in lines[:-1:997]])
             assert (np.diff(pos) > 0).all()
     assert len(set(digests.values())) == 1, digests   # read-major / column-major / chained single-launch kernels, TMA / vector / direct-to-HBM stores all agree
+
+
+# ---------------------------------------------------------------- htslib-compatible iterator tier (T1)
+COMPAT = os.path.join(ROOT, 'tests', 'compat', '_build', 'plp_dump')
+
+
+@pytest.mark.parametrize('args,files', [
+    ([], ['test/mpileup/mp_DI.sam']), ([], ['test/mpileup/mp_P.sam']), ([], ['test/mpileup/mp_N2.sam']),
+    (['-o'], ['test/mpileup/overlap50.sam']), ([], ['test/mpileup/mpileup.1.bam']), (['-o'], ['test/mpileup/mpileup.1.bam']),
+    ([], ['test/mpileup/xx#depth1.sam', 'test/mpileup/xx#depth2.sam']), (['-d', '8500'], ['test/mpileup/deep.sam']),
+    ([], ['test/dat/mpileup.1.sam', 'test/dat/mpileup.2.sam', 'test/dat/mpileup.3.sam']),
+], ids=['DI', 'P', 'N2', 'overlap50', 'mpileup1', 'mpileup1-overlaps', 'two-files', 'maxcnt8500', 'three-files'])
+def test_htslib_compat_iterator(args, files, oracle_bin, corpus):
+    """bam_mplp64_auto() through the GPU engine == the oracle's restatement of htslib's iterator,
+    field by field (qpos, indel, is_del/head/tail/refskip, cigar_ind, quality seen through p->b, insertion text)."""
+    assert os.path.exists(COMPAT), 'tests/compat/_build/plp_dump missing: run python samtools_b200/build.py'
+    paths = [os.path.join(corpus, f) for f in files]
+    got = subprocess.run([COMPAT, *args, *paths], capture_output=True)
+    want = subprocess.run([oracle_bin, 'pileup-dump', *args, *paths], capture_output=True)
+    assert got.returncode == 0, got.stderr[-300:]
+    assert got.stdout == want.stdout
+    assert len(got.stdout) > 100
