@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(TILE) k_mpileup_write(MpFmt fmt, const uint32_
 }
 
 #include "mpileup_rm.cuh"
+#include "mpileup_w4.cuh"
 
 // depth rows "name\tpos(\tdepth)*\n" (bam2depth.c:234-244)
 struct DpFmt {
@@ -595,11 +596,12 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
     s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
-    s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + column-major write (default), 1: column-major both, 2: read-major both
+    s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + 4-columns-per-thread write (default), 1: column-major both, 2: read-major both, 3: read-major sizing + 1-column-per-thread write
     if (e->chained) e->variant = 1;
     e->smem_text_rm = 36 * 1024;
     s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text_rm = (uint32_t)atoi(s);
     cudaFuncSetAttribute(k_mp_rm_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text_rm + 16);
+    cudaFuncSetAttribute(k_mpileup_write4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text_rm + 16);
     cudaFuncSetAttribute(k_mpileup_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_depth_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_mpileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
@@ -929,6 +931,10 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
     if (e->variant == 2) {
         k_mp_rm_write<<<ntr, RM_WARPS * 32, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
+                                                                              e->smem_text_rm, e->use_tma);
+    } else if (e->variant == 0 && e->n_files == 1 && !c->out_mapq && !c->out_qpos && !c->out_qpos5) {
+        // the standard line: four adjacent columns per thread
+        k_mpileup_write4<<<ntr, W4_THREADS, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
                                                                               e->smem_text_rm, e->use_tma);
     } else {
         const int ntw = (ncols + TILE - 1) / TILE;
