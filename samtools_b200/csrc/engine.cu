@@ -596,7 +596,7 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
     s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
-    s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + 4-columns-per-thread write (default), 1: column-major both, 2: read-major both, 3: read-major sizing + 1-column-per-thread write
+    s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + one-column-per-thread write (default), 1: column-major both, 2: read-major both, 4: read-major sizing + 4-columns-per-thread write
     if (e->chained) e->variant = 1;
     e->smem_text_rm = 36 * 1024;
     s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text_rm = (uint32_t)atoi(s);
@@ -932,8 +932,9 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     if (e->variant == 2) {
         k_mp_rm_write<<<ntr, RM_WARPS * 32, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
                                                                               e->smem_text_rm, e->use_tma);
-    } else if (e->variant == 0 && e->n_files == 1 && !c->out_mapq && !c->out_qpos && !c->out_qpos5) {
-        // the standard line: four adjacent columns per thread
+    } else if (e->variant == 4 && e->n_files == 1 && !c->out_mapq && !c->out_qpos && !c->out_qpos5) {
+        // experimental: four adjacent columns per thread (fewer instructions per entry, but the 128 columns a warp
+        // stages in shared memory cap occupancy at ~14 warps/SM: measured slower than one column per thread)
         k_mpileup_write4<<<ntr, W4_THREADS, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
                                                                               e->smem_text_rm, e->use_tma);
     } else {
