@@ -35,8 +35,12 @@ __device__ __forceinline__ int ref_code(const RawSoA &r, int64_t p)
 }
 
 // which reads need the HMM, their reference window and band (sam_prob_realn prologue)
-__global__ void k_baq_plan(RawSoA r, b200_stage_conf_t cf, const uint8_t *state, BaqPlan *plan, int32_t *idx,
-                           unsigned long long *counters /* [0]=count, [1]=max slab doubles, [2]=max lq */)
+constexpr int TPR_BW = 7;            // band of the thread-per-read kernel (the default band of sam_prob_realn)
+constexpr int TPR_PITCH = 52;        // doubles per row: (2*7+1)*3 + 6 = 51, padded
+constexpr int TPR_MAX_LQ = 512;
+
+__global__ void k_baq_plan(RawSoA r, b200_stage_conf_t cf, const uint8_t *state, BaqPlan *plan, int32_t *idx, int32_t *idx2, int use_tpr,
+                           unsigned long long *counters /* [0]=count, [1]=max slab doubles, [2]=max lq, [3]=count2, [4]=max lq of list 2 */)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= r.n) return;
@@ -72,9 +76,15 @@ __global__ void k_baq_plan(RawSoA r, b200_stage_conf_t cf, const uint8_t *state,
     int64_t d2 = l_ref - lq; if (d2 < 0) d2 = -d2;
     if (b2 < d2) b2 = (int)d2;
     BaqPlan p; p.xb = xb; p.l_ref = (int32_t)l_ref; p.bw = b2;
+    plan[i] = p;
+    if (use_tpr && b2 <= TPR_BW && lq <= TPR_MAX_LQ) {     // common shape: one thread per read (k_baq_tpr)
+        const unsigned long long slot2 = atomicAdd(&counters[3], 1ULL);
+        idx2[slot2] = (int32_t)i;
+        atomicMax(&counters[4], (unsigned long long)lq);
+        return;
+    }
     const unsigned long long slot = atomicAdd(&counters[0], 1ULL);
     idx[slot] = (int32_t)i;
-    plan[i] = p;
     const unsigned long long stride = (unsigned long long)(2 * b2 + 1) * 3 + 6;
     const unsigned long long slab = (unsigned long long)(lq + 1) * stride + 2 * stride + (unsigned long long)lq + 2 + (unsigned long long)lq + 8;
     atomicMax(&counters[1], slab);
@@ -350,6 +360,215 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Thread-per-read BAQ for the common shape (band <= 7, l_qseq <= 512).  The recurrences are the
+// scalar loops of probaln_glocal verbatim (same order of every product and sum, so bit-exact by
+// construction); what is GPU-specific is the storage: the forward matrix, the two backward rows
+// and the scaling vector of the 32 reads of a warp are interleaved read-minor ("cell (i,u) of
+// lane l" lives at ((i*PITCH+u)*32 + l)), so every load/store of a warp is one coalesced
+// 256-byte request even though each thread walks its own matrix.  Cells just outside the band
+// that the next row (or the same row's D chain) will look at are zeroed explicitly -- the role
+// calloc plays in the reference.  No shuffles, no redundant lanes: ~28x fewer warp-instructions
+// per read than the warp-per-read kernel, which remains the path for wide bands / long reads.
+#define TF(i, u) fb[((size_t)(i) * TPR_PITCH + (size_t)(u)) * 32]
+#define TBROW(rw, u) bb[((size_t)(rw) * TPR_PITCH + (size_t)(u)) * 32]
+#define TS(i) sbv[(size_t)(i) * 32]
+#define TI(arr, j) ib[((size_t)(arr) * lqmax + (size_t)(j)) * 32]
+#define TPR_SET_U(u, b, i, k) { int x_ = (i) - (b); x_ = x_ > 0 ? x_ : 0; (u) = ((k) - x_ + 1) * 3; }
+
+__global__ void __launch_bounds__(128) k_baq_tpr(RawSoA r, const BaqPlan *plan, const int32_t *idx, int64_t n_idx, double *slabs,
+                                                 unsigned long long slab_doubles, int lqmax, const double *q2p, const double *qthr)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_thr = (int64_t)gridDim.x * blockDim.x;
+    double *slab = slabs + (size_t)gw * slab_doubles;
+    double *fb = slab + lane;                                                  // forward matrix, (lqmax+1) rows
+    double *bb = slab + (size_t)(lqmax + 1) * TPR_PITCH * 32 + lane;          // two backward rows
+    double *sbv = slab + (size_t)(lqmax + 3) * TPR_PITCH * 32 + lane;         // scaling factors s[0..lq+1]
+    int32_t *ib = (int32_t *)(slab + (size_t)(lqmax + 3) * TPR_PITCH * 32 + (size_t)(lqmax + 2) * 32) + lane;   // 5 int arrays of lqmax
+    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_idx; wi += n_thr) {
+        const int64_t ri = idx[wi];
+        const BaqPlan pl = plan[ri];
+        const int l_query = r.l_qseq[ri], l_ref = pl.l_ref, bw = pl.bw;
+        uint8_t *qual = r.qual + r.qual_off[ri];
+        const uint32_t qoff = (uint32_t)r.qual_off[ri];
+        const double cd = 0.001, ce = 0.1;
+        const double sM = 1. / (2 * l_query + 2), sI = sM;
+        double m[9];
+        m[0] = (1 - cd - cd) * (1 - sM); m[1] = m[2] = cd * (1 - sM);
+        m[3] = (1 - ce) * (1 - sI); m[4] = ce * (1 - sI); m[5] = 0.;
+        m[6] = 1 - ce; m[7] = 0.; m[8] = ce;
+        const double bM = (1 - cd) / l_ref, bI = cd / l_ref;
+        int i, k;
+        TS(0) = 1.;
+        /*** forward ***/
+        {   // row 1
+            double sum = 0.;
+            const int beg = 1, end = l_ref < bw + 1 ? l_ref : bw + 1;
+            const int qc = nt16_int_of(base4(r.seq4, qoff, 0));
+            const double q0 = (double)(float)q2p[qual[0]];
+            int u0; TPR_SET_U(u0, bw, 1, beg);
+            TF(1, u0 - 3) = 0.; TF(1, u0 - 2) = 0.; TF(1, u0 - 1) = 0.;
+            for (k = beg; k <= end; ++k) {
+                int u; TPR_SET_U(u, bw, 1, k);
+                const double e = emis(ref_code(r, pl.xb + k - 1), qc, q0);
+                const double a = e * bM, b = BAQ_EI * bI;
+                TF(1, u) = a; TF(1, u + 1) = b; TF(1, u + 2) = 0.;
+                sum += a + b;
+            }
+            { int u; TPR_SET_U(u, bw, 1, end); TF(1, u + 3) = 0.; TF(1, u + 4) = 0.; TF(1, u + 5) = 0.; }
+            TS(1) = sum;
+            for (k = beg; k <= end; ++k) { int u; TPR_SET_U(u, bw, 1, k); TF(1, u) /= sum; TF(1, u + 1) /= sum; TF(1, u + 2) /= sum; }
+        }
+        for (i = 2; i <= l_query; ++i) {
+            const int qyi = nt16_int_of(base4(r.seq4, qoff, i - 1));
+            const double qli = (double)(float)q2p[qual[i - 1]];
+            int beg = 1, end = l_ref, x;
+            x = i - bw; beg = beg > x ? beg : x;
+            x = i + bw; end = end < x ? end : x;
+            double sum = 0.;
+            int u0; TPR_SET_U(u0, bw, i, beg);
+            TF(i, u0 - 3) = 0.; TF(i, u0 - 2) = 0.; TF(i, u0 - 1) = 0.;
+            double pM = 0., pD = 0.;                    // fi[v01+0], fi[v01+2]: the cell to the left in this row (unscaled)
+            for (k = beg; k <= end; ++k) {
+                int u, v11, v10;
+                TPR_SET_U(u, bw, i, k); TPR_SET_U(v11, bw, i - 1, k - 1); TPR_SET_U(v10, bw, i - 1, k);
+                const double e = emis(ref_code(r, pl.xb + k - 1), qyi, qli);
+                const double M = e * (m[0] * TF(i - 1, v11) + m[3] * TF(i - 1, v11 + 1) + m[6] * TF(i - 1, v11 + 2));
+                const double I = BAQ_EI * (m[1] * TF(i - 1, v10) + m[4] * TF(i - 1, v10 + 1));
+                const double D = m[2] * pM + m[8] * pD;
+                TF(i, u) = M; TF(i, u + 1) = I; TF(i, u + 2) = D;
+                sum += M + I + D;
+                pM = M; pD = D;
+            }
+            { int u; TPR_SET_U(u, bw, i, end); TF(i, u + 3) = 0.; TF(i, u + 4) = 0.; TF(i, u + 5) = 0.; }
+            TS(i) = sum;
+            const double inv = 1. / sum;
+            for (k = beg; k <= end; ++k) { int u; TPR_SET_U(u, bw, i, k); TF(i, u) *= inv; TF(i, u + 1) *= inv; TF(i, u + 2) *= inv; }
+        }
+        double s_last;
+        {   // termination
+            double sum = 0.;
+            for (k = 1; k <= l_ref; ++k) {
+                int u; TPR_SET_U(u, bw, l_query, k);
+                if (u < 3 || u >= (bw * 2 + 1) * 3 + 3) continue;
+                int beg = 1, end = l_ref, x;
+                x = l_query - bw; beg = beg > x ? beg : x;
+                x = l_query + bw; end = end < x ? end : x;
+                if (l_query == 1) end = l_ref < bw + 1 ? l_ref : bw + 1;
+                if (k < beg || k > end) continue;          // cells never written hold zero in the reference: adding 0 changes nothing
+                sum += TF(l_query, u) * sM + TF(l_query, u + 1) * sI;
+            }
+            s_last = sum;
+            TS(l_query + 1) = sum;
+        }
+        /*** backward + MAP ***/
+        int cur = 0;                                      // row buffer holding row i; 1-cur holds row i+1
+        {
+            const double s_lq = TS(l_query);
+            int beg = 1, end = l_ref, x;
+            x = l_query - bw; beg = beg > x ? beg : x;
+            x = l_query + bw; end = end < x ? end : x;
+            if (l_query == 1) end = l_ref < bw + 1 ? l_ref : bw + 1;
+            int u0; TPR_SET_U(u0, bw, l_query, beg);
+            TBROW(cur, u0 - 3) = 0.; TBROW(cur, u0 - 2) = 0.; TBROW(cur, u0 - 1) = 0.;
+            for (k = beg; k <= end; ++k) {
+                int u; TPR_SET_U(u, bw, l_query, k);
+                TBROW(cur, u) = sM / s_lq / s_last; TBROW(cur, u + 1) = sI / s_lq / s_last; TBROW(cur, u + 2) = 0.;
+            }
+            { int u; TPR_SET_U(u, bw, l_query, end); TBROW(cur, u + 3) = 0.; TBROW(cur, u + 4) = 0.; TBROW(cur, u + 5) = 0.; }
+        }
+        for (i = l_query; i >= 1; --i) {
+            int beg = 1, end = l_ref, x;
+            x = i - bw; beg = beg > x ? beg : x;
+            x = i + bw; end = end < x ? end : x;
+            if (i < l_query) {
+                const int nxt = cur; cur = 1 - cur;          // nxt holds row i+1
+                const double y = (i > 1) ? 1. : 0.;
+                const int qyi1 = nt16_int_of(base4(r.seq4, qoff, i));
+                const double qli1 = (double)(float)q2p[qual[i]];
+                { int u; TPR_SET_U(u, bw, i, end); TBROW(cur, u + 3) = 0.; TBROW(cur, u + 4) = 0.; TBROW(cur, u + 5) = 0.; }
+                double nD = 0.;                              // bi[v01+2]: D of the cell to the right in this row (already times y)
+                for (k = end; k >= beg; --k) {
+                    int u, v11, v10;
+                    TPR_SET_U(u, bw, i, k); TPR_SET_U(v11, bw, i + 1, k + 1); TPR_SET_U(v10, bw, i + 1, k);
+                    const double e = (k >= l_ref ? 0. : emis(ref_code(r, pl.xb + k), qyi1, qli1)) * TBROW(nxt, v11);
+                    const double b10 = TBROW(nxt, v10 + 1);
+                    const double B0 = e * m[0] + BAQ_EI * m[1] * b10 + m[2] * nD;
+                    const double B1 = e * m[3] + BAQ_EI * m[4] * b10;
+                    const double B2 = (e * m[6] + m[8] * nD) * y;
+                    TBROW(cur, u) = B0; TBROW(cur, u + 1) = B1; TBROW(cur, u + 2) = B2;
+                    nD = B2;
+                }
+                { int u; TPR_SET_U(u, bw, i, beg); TBROW(cur, u - 3) = 0.; TBROW(cur, u - 2) = 0.; TBROW(cur, u - 1) = 0.; }
+                const double ys = 1. / TS(i);
+                for (k = beg; k <= end; ++k) { int u; TPR_SET_U(u, bw, i, k); TBROW(cur, u) *= ys; TBROW(cur, u + 1) *= ys; TBROW(cur, u + 2) *= ys; }
+            }
+            // MAP of row i
+            double sum = 0., mx = 0.; int max_k = -1;
+            const int fend = (i == 1) ? (l_ref < bw + 1 ? l_ref : bw + 1) : end;
+            for (k = beg; k <= end; ++k) {
+                int u; TPR_SET_U(u, bw, i, k);
+                const bool inF = k <= fend;
+                double z = (inF ? TF(i, u) : 0.) * TBROW(cur, u);
+                if (z > mx) { mx = z; max_k = (k - 1) << 2 | 0; }
+                sum += z;
+                z = (inF ? TF(i, u + 1) : 0.) * TBROW(cur, u + 1);
+                if (z > mx) { mx = z; max_k = (k - 1) << 2 | 1; }
+                sum += z;
+            }
+            mx /= sum;
+            TI(0, i - 1) = max_k;
+            const double xx = 1. - mx;
+            int kq;
+            if (!(xx > 0.)) kq = 0;
+            else {
+                int lo_ = 0, hi_ = 101;
+                while (lo_ < hi_) { const int mid = (lo_ + hi_ + 1) >> 1; if (xx <= qthr[mid]) lo_ = mid; else hi_ = mid - 1; }
+                kq = lo_ > 100 ? 99 : lo_;
+            }
+            TI(1, i - 1) = kq;
+        }
+        // ---- sam_prob_realn epilogue (EXTEND + APPLY)
+        {
+            const int lq = l_query;
+            for (int j = 0; j < lq; ++j) TI(2, j) = qual[j];
+            const uint32_t *cg = r.cigar + r.cigar_off[ri];
+            int64_t x = r.pos[ri]; int y = 0;
+            for (int kk = 0; kk < (int)r.n_cigar[ri]; ++kk) {
+                const int op = cg[kk] & 0xf; int l = (int)(cg[kk] >> 4);
+                if (is_mop(op)) {
+                    if (l > lq - y) l = lq - y;
+                    if (l > 0) {
+                        for (int j = y; j < y + l; ++j) {
+                            const int st = TI(0, j);
+                            TI(2, j) = ((st & 3) != 0 || (int64_t)(st >> 2) != x - pl.xb + (j - y)) ? 0 : TI(1, j);
+                        }
+                        TI(3, y) = TI(2, y);
+                        for (int j = y + 1; j < y + l; ++j) { const int a = TI(2, j), b = TI(3, j - 1); TI(3, j) = a > b ? a : b; }
+                        TI(4, y + l - 1) = TI(2, y + l - 1);
+                        for (int j = y + l - 2; j >= y; --j) { const int a = TI(2, j), b = TI(4, j + 1); TI(4, j) = a > b ? a : b; }
+                        for (int j = y; j < y + l; ++j) { const int a = TI(3, j), b = TI(4, j); TI(2, j) = a < b ? a : b; }
+                    }
+                    x += l; y += l;
+                } else if (op == OP_S || op == OP_I) { if (l > lq - y) l = lq - y; y += l; }
+                else if (op == OP_D) x += l;
+            }
+            for (int j = 0; j < lq; ++j) {
+                const int qv = qual[j], bq = TI(2, j);
+                const int adj = qv <= bq ? 0 : qv - bq;
+                qual[j] = (uint8_t)(qv - adj);
+            }
+        }
+    }
+}
+#undef TF
+#undef TBROW
+#undef TS
+#undef TI
+
 // host: tables with the box's own libm (what the reference binary would use here)
 static void baq_host_tables(double *q2p, double *qthr)
 {
@@ -376,31 +595,47 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
         CK(cudaMemcpyAsync(e->d_qthr, qthr, sizeof qthr, cudaMemcpyHostToDevice, e->stream));
         CK(cudaStreamSynchronize(e->stream));
     }
-    // BaqPlan array reuses a byte buffer
+    // plan array + two index lists share one buffer
     size_t plan_bytes = (size_t)(n + 1) * sizeof(BaqPlan);
-    if (ensure(e, e->baq_idx, e->cap_baq_idx, (size_t)n + 1 + plan_bytes / 4 + 4)) return -1;
-    int32_t *idx = e->baq_idx;
-    BaqPlan *plan = (BaqPlan *)(e->baq_idx + ((n + 1 + 3) & ~3LL));
-    CK(cudaMemsetAsync(e->d_misc + 16, 0, 4 * 8, e->stream));
-    k_baq_plan<<<nblk(n, 256), 256, 0, e->stream>>>(r, cf, e->state, plan, idx, e->d_misc + 16); e->launches++;
-    unsigned long long h[3];
+    const int64_t nr = (n + 1 + 3) & ~3LL;
+    if (ensure(e, e->baq_idx, e->cap_baq_idx, (size_t)(2 * nr) + plan_bytes / 4 + 4)) return -1;
+    int32_t *idx = e->baq_idx, *idx2 = e->baq_idx + nr;
+    BaqPlan *plan = (BaqPlan *)(e->baq_idx + 2 * nr);
+    static const int use_tpr = getenv("B200_BAQ_TPR") ? atoi(getenv("B200_BAQ_TPR")) : 1;
+    CK(cudaMemsetAsync(e->d_misc + 16, 0, 16 * 8, e->stream));
+    k_baq_plan<<<nblk(n, 256), 256, 0, e->stream>>>(r, cf, e->state, plan, idx, idx2, use_tpr, e->d_misc + 16); e->launches++;
+    unsigned long long h[5];
     CK(cudaMemcpyAsync(h, e->d_misc + 16, sizeof h, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
-    const int64_t n_idx = (int64_t)h[0];
-    if (n_idx == 0) return 0;
-    const unsigned long long slab = h[1] + 2 * h[2] / 8 + 8;   // + left/right byte rows
-    // resident warps: 4 per block, up to 16 blocks/SM, bounded by ~2 GB of slabs and by the work
-    int64_t warps = (int64_t)e->n_sm * 12 * 4;   // 48 warps per SM (register-limited), each latency-bound: occupancy is the lever
-    const int64_t cap = (int64_t)((6ULL << 30) / (slab * 8));
-    if (warps > cap) warps = cap;
-    if (warps > n_idx) warps = n_idx;
-    if (warps < 1) warps = 1;
-    const int blocks = (int)((warps + 3) / 4);
-    warps = (int64_t)blocks * 4;
-    if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab)) return -1;
-    // the order in which reads are picked does not matter; sort-free
-    k_baq<<<blocks, 128, 0, e->stream>>>(r, plan, idx, n_idx, e->baq_f, slab, e->d_q2p, e->d_qthr, e->d_misc + 19); e->launches++;
+    const int64_t n_idx = (int64_t)h[0], n_idx2 = (int64_t)h[3];
+    if (n_idx2 > 0) {   // common shape: one thread per read
+        const int lqmax = (int)h[4];
+        const unsigned long long slab = ((unsigned long long)(lqmax + 3) * TPR_PITCH + (unsigned long long)(lqmax + 2) + (5ULL * lqmax + 1) / 2 + 4) * 32;
+        int64_t warps = (int64_t)e->n_sm * 32;
+        const int64_t cap = (int64_t)((24ULL << 30) / (slab * 8));
+        if (warps > cap) warps = cap;
+        if (warps > (n_idx2 + 31) / 32) warps = (n_idx2 + 31) / 32;
+        if (warps < 1) warps = 1;
+        const int blocks = (int)((warps + 3) / 4);
+        warps = (int64_t)blocks * 4;
+        if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab)) return -1;
+        k_baq_tpr<<<blocks, 128, 0, e->stream>>>(r, plan, idx2, n_idx2, e->baq_f, slab, lqmax, e->d_q2p, e->d_qthr); e->launches++;
+        CK(cudaGetLastError());
+    }
+    if (n_idx > 0) {    // wide bands / long reads: one warp per read
+        const unsigned long long slab = h[1] + 2 * h[2] / 8 + 8;   // + left/right byte rows
+        int64_t warps = (int64_t)e->n_sm * 12 * 4;
+        const int64_t cap = (int64_t)((6ULL << 30) / (slab * 8));
+        if (warps > cap) warps = cap;
+        if (warps > n_idx) warps = n_idx;
+        if (warps < 1) warps = 1;
+        const int blocks = (int)((warps + 3) / 4);
+        warps = (int64_t)blocks * 4;
+        if (n_idx2 > 0) CK(cudaStreamSynchronize(e->stream));   // the slab buffer is shared by the two kernels
+        if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab)) return -1;
+        k_baq<<<blocks, 128, 0, e->stream>>>(r, plan, idx, n_idx, e->baq_f, slab, e->d_q2p, e->d_qthr, e->d_misc + 19 + 8); e->launches++;
+    }
     CK(cudaGetLastError());
     return 0;
 }

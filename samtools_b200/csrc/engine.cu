@@ -401,6 +401,12 @@ __global__ void __launch_bounds__(TILE) k_mpileup_write(MpFmt fmt, const uint32_
 {
     text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
 }
+// same kernel compiled for 12 resident CTAs per SM (<= 40 registers): the loop is latency-bound, occupancy pays
+__global__ void __launch_bounds__(TILE, 12) k_mpileup_write_occ(MpFmt fmt, const uint32_t *len, const MpFileSz *st, const uint64_t *tile_base,
+                                                               char *out, uint32_t smem_cap, int use_tma)
+{
+    text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
+}
 
 #include "mpileup_rm.cuh"
 #include "mpileup_w4.cuh"
@@ -596,6 +602,8 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
     s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
+    s = getenv("B200_PLP_WRITE_OCC"); e->write_occ = s ? atoi(s) : 0;
+    cudaFuncSetAttribute(k_mpileup_write_occ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + one-column-per-thread write (default), 1: column-major both, 2: read-major both, 4: read-major sizing + 4-columns-per-thread write
     if (e->chained) e->variant = 1;
     e->smem_text_rm = 36 * 1024;
@@ -939,7 +947,8 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
                                                                               e->smem_text_rm, e->use_tma);
     } else {
         const int ntw = (ncols + TILE - 1) / TILE;
-        k_mpileup_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        if (e->write_occ) k_mpileup_write_occ<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        else k_mpileup_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
     }
     e->launches++;
     CK(cudaEventRecord(e->ev1, e->stream));
