@@ -247,7 +247,7 @@ def main():
 
     # ---- device-resident: K column-stage passes
     eng.stage(soa, sconf)
-    kernel_ms = []
+    kernel_ms, parts_ms = [], []
     with ClockSampler(local) as clk:
         sync_all()
         l0 = eng.launches
@@ -255,6 +255,7 @@ def main():
         for _ in range(args.steps):
             step_device()
             kernel_ms.append(eng.last_kernel_ms)
+            parts_ms.append(eng.last_mpileup_parts_ms)
         sync_all()
         dt = time.perf_counter() - t0
         launches = eng.launches - l0
@@ -270,8 +271,17 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         kms = float(np.mean(kernel_ms))
+        size_ms, scan_ms, write_ms = [float(x) for x in np.mean(np.array(parts_ms), axis=0)]
+        # dominant kernel = the write pass: it re-reads every staged read (descriptor, qualities, bases) and
+        # writes every text byte once -> its algorithmic bytes are bytes_in + bytes_out
         alg = bytes_in + out_len
-        achieved = alg / (kms * 1e-3) / 1e9
+        achieved = alg / (write_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            if abs(tj.get('region_mb', 0) - args.region_mb) < 1e-9:
+                traffic = tj.get('k_mpileup_write_dram_bytes')
         value = world * ncols * args.steps / dt
         e2e = world * ncols * args.steps / dt_e2e
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -280,9 +290,11 @@ def main():
                 'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(out_len), 'ms_per_step': 1e3 * dt_e2e / args.steps,
                         'handles': n_h},
                 'gpu_launches': int(launches),
-                'roofline': {'bound': 'hbm', 'kernel': 'k_mpileup', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                             'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(alg),
-                             'bytes_in': int(bytes_in), 'bytes_out': int(out_len), 'kernel_ms': kms},
+                'roofline': {'bound': 'hbm', 'kernel': 'k_mpileup_write', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                             'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(alg),
+                             'bytes_in': int(bytes_in), 'bytes_out': int(out_len), 'kernel_ms': write_ms,
+                             'step_kernels_ms': {'k_mp_rm_size': size_ms, 'k_scan_u32_to_u64': scan_ms, 'k_mpileup_write': write_ms, 'total': kms},
+                             'step_frac': alg / (kms * 1e-3) / 1e9 / peak},
                 'reads_per_step_per_gpu': n_reads}
         if world == 1 and not args.no_cpu_baseline:
             exe = oracle_path()

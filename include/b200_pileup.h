@@ -189,6 +189,8 @@ int b200_pileup_entries(b200_engine_t *e, int32_t file, int64_t beg, int64_t end
 double b200_last_kernel_ms(const b200_engine_t *e);
 double b200_last_stage_ms(const b200_engine_t *e);
 int64_t b200_launch_count(const b200_engine_t *e);   /* kernels launched by this handle so far */
+/* last b200_mpileup_text(): device time of its three launches -- sizing kernel, tile-offset scan, write kernel */
+void b200_last_mpileup_parts_ms(const b200_engine_t *e, double *ms3);
 
 #ifdef __cplusplus
 }

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
 #define TI(arr, j) ib[((size_t)(arr) * lqmax + (size_t)(j)) * 32]
 #define TPR_SET_U(u, b, i, k) { int x_ = (i) - (b); x_ = x_ > 0 ? x_ : 0; (u) = ((k) - x_ + 1) * 3; }
 
-__global__ void __launch_bounds__(128) k_baq_tpr(RawSoA r, const BaqPlan *plan, const int32_t *idx, int64_t n_idx, double *slabs,
+__global__ void __launch_bounds__(128, 8) k_baq_tpr(RawSoA r, const BaqPlan *plan, const int32_t *idx, int64_t n_idx, double *slabs,
                                                  unsigned long long slab_doubles, int lqmax, const double *q2p, const double *qthr)
 {
     const int lane = threadIdx.x & 31;

@@ -577,6 +577,7 @@ extern "C" const char *b200_last_error(const b200_engine_t *e) { return e ? e->e
 extern "C" double b200_last_kernel_ms(const b200_engine_t *e) { return e->last_kernel_ms; }
 extern "C" double b200_last_stage_ms(const b200_engine_t *e) { return e->last_stage_ms; }
 extern "C" int64_t b200_launch_count(const b200_engine_t *e) { return e->launches; }
+extern "C" void b200_last_mpileup_parts_ms(const b200_engine_t *e, double *ms3) { for (int i = 0; i < 3; ++i) ms3[i] = e->last_parts_ms[i]; }
 
 extern "C" int b200_engine_create(int device, b200_engine_t **out)
 {
@@ -596,7 +597,7 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
         delete e;
         return -1;
     }
-    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1); cudaEventCreate(&e->evA); cudaEventCreate(&e->evB);
     cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
     e->smem_text = 24 * 1024;
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
@@ -627,7 +628,7 @@ extern "C" void b200_engine_destroy(b200_engine_t *e)
     cudaStreamSynchronize(e->stream);
     e->free_all();
     cudaFree(e->d_acc); cudaFree(e->d_misc);
-    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+    cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->evA); cudaEventDestroy(e->evB);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -936,7 +937,9 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
     k_mp_rm_size<<<ntr, RM_WARPS * 32, 0, e->stream>>>(fmt.v, fmt.cf, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
+    CK(cudaEventRecord(e->evA, e->stream));
     k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
+    CK(cudaEventRecord(e->evB, e->stream));
     if (e->variant == 2) {
         k_mp_rm_write<<<ntr, RM_WARPS * 32, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
                                                                               e->smem_text_rm, e->use_tma);
@@ -957,6 +960,9 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
+    cudaEventElapsedTime(&ms, e->ev0, e->evA); e->last_parts_ms[0] = ms;      // sizing kernel
+    cudaEventElapsedTime(&ms, e->evA, e->evB); e->last_parts_ms[1] = ms;      // tile-offset scan
+    cudaEventElapsedTime(&ms, e->evB, e->ev1); e->last_parts_ms[2] = ms;      // write kernel
     if (total > bound) { snprintf(e->err, sizeof e->err, "internal: output %llu exceeds bound %llu", total, (unsigned long long)bound); return -1; }
     *out_len = (size_t)total; e->last_out_len = (size_t)total;
     if (out) {

@@ -19,7 +19,7 @@ POS_MAX = (0x7fffffff << 32) | 0xffffffff
 EXPORTS = ['b200_engine_create', 'b200_engine_destroy', 'b200_last_error', 'b200_version', 'b200_stage',
            'b200_mpileup_text', 'b200_depth_text', 'b200_coverage', 'b200_glf', 'b200_fetch_qual',
            'b200_fetch_mapq_keep', 'b200_pileup_entries', 'b200_last_kernel_ms', 'b200_last_stage_ms',
-           'b200_launch_count']
+           'b200_launch_count', 'b200_last_mpileup_parts_ms']
 
 
 class Batch(C.Structure):
@@ -93,6 +93,7 @@ def load_library():
         lib.b200_last_kernel_ms.argtypes = [C.c_void_p]; lib.b200_last_kernel_ms.restype = C.c_double
         lib.b200_last_stage_ms.argtypes = [C.c_void_p]; lib.b200_last_stage_ms.restype = C.c_double
         lib.b200_launch_count.argtypes = [C.c_void_p]; lib.b200_launch_count.restype = C.c_int64
+        lib.b200_last_mpileup_parts_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double * 3)]
         _lib = lib
     return _lib
 
@@ -228,6 +229,12 @@ class Engine:
     @property
     def last_stage_ms(self):
         return self.lib.b200_last_stage_ms(self.h)
+
+    @property
+    def last_mpileup_parts_ms(self):
+        a = (C.c_double * 3)()
+        self.lib.b200_last_mpileup_parts_ms(self.h, C.byref(a))
+        return list(a)
 
     @property
     def launches(self):

@@ -38,6 +38,7 @@ const char *b200_last_error(const b200_engine_t *e) { return e->err.c_str(); }
 double b200_last_kernel_ms(const b200_engine_t *) { return 0; }
 double b200_last_stage_ms(const b200_engine_t *) { return 0; }
 int64_t b200_launch_count(const b200_engine_t *) { return 0; }
+void b200_last_mpileup_parts_ms(const b200_engine_t *, double *ms3) { ms3[0] = ms3[1] = ms3[2] = 0; }
 int b200_engine_create(int, b200_engine_t **out) { *out = new b200_engine(); return 0; }
 void b200_engine_destroy(b200_engine_t *e) { delete e; }
 
