@@ -46,43 +46,53 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """SM clock + throttle reasons of one GPU, polled through NVML every few ms while the timed
+    regions run (the recipe's nvidia-smi query, without the process start-up latency)."""
+    REASONS = (('hw_slowdown', 0x8), ('sw_power_cap', 0x4), ('sw_thermal_slowdown', 0x20), ('hw_thermal_slowdown', 0x40))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period=0.004):
+        self.index, self.period, self.rows, self.stop = index, period, [], False
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100', '-i', str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
-        except OSError:
-            self.proc = None
+        if self.h is not None:
+            self.t = threading.Thread(target=self._poll, daemon=True); self.t.start()
         return self
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.rows.append(ln.strip().split(', '))
-
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.stop = True
+        if self.h is not None:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx = max(mx, float(r[2]))
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
-                    if v.strip().lower().startswith('active'):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                pass
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons), 'samples': len(sm)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({name for _, bits in self.rows for name, mask in self.REASONS if bits & mask})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': getattr(self, 'max_mhz', None), 'reasons': reasons,
+                'samples': len(sm), 'source': 'nvml, polled during the timed regions'}
 
 
 def oracle_path():
