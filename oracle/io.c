@@ -230,9 +230,13 @@ reader_t *reader_open(const char *fn, const char *fai)
     int c0 = gzgetc(rd->fp);
     if (c0 < 0) { rd->h->text = strdup(""); return rd; } /* empty input */
     gzungetc(c0, rd->fp);
-    if (c0 == 'B') {
-        char magic[4];
-        if (gzread(rd->fp, magic, 4) != 4 || memcmp(magic, "BAM\1", 4)) goto fail;
+    int is_bam = 0;
+    if (c0 == 'B') {   /* "BAM\1" magic, or a SAM record whose name starts with B: look at four bytes */
+        char magic[4]; int got = gzread(rd->fp, magic, 4), j;
+        if (got == 4 && memcmp(magic, "BAM\1", 4) == 0) is_bam = 1;
+        else for (j = got - 1; j >= 0; j--) gzungetc((unsigned char)magic[j], rd->fp);
+    }
+    if (is_bam) {
         rd->is_bam = 1;
         int32_t l_text, n_ref, i;
         if (rd_i32(rd->fp, &l_text)) goto fail;

@@ -151,9 +151,15 @@ std::unique_ptr<AlnReader> AlnReader::open(const std::string &path, const std::s
     if (c0 < 0) return rd;
     gzungetc(c0, fp);
     auto add_ref = [&](const std::string &n, int64_t l) { rd->hdr_.names.push_back(n); rd->hdr_.lens.push_back(l); };
-    if (c0 == 'B') {
-        char magic[4]; int32_t l_text, n_ref;
-        if (gzread(fp, magic, 4) != 4 || memcmp(magic, "BAM\1", 4) || gzread(fp, &l_text, 4) != 4) return nullptr;
+    bool bam = false;
+    if (c0 == 'B') {   // "BAM\1" magic, or a SAM record whose name starts with B: look at four bytes
+        char magic[4]; int got = gzread(fp, magic, 4);
+        if (got == 4 && memcmp(magic, "BAM\1", 4) == 0) bam = true;
+        else for (int j = got - 1; j >= 0; --j) gzungetc((unsigned char)magic[j], fp);
+    }
+    if (bam) {
+        int32_t l_text, n_ref;
+        if (gzread(fp, &l_text, 4) != 4) return nullptr;
         rd->is_bam_ = true;
         rd->hdr_.text.resize((size_t)l_text);
         if (l_text && gzread(fp, &rd->hdr_.text[0], (unsigned)l_text) != l_text) return nullptr;

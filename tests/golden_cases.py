@@ -39,7 +39,28 @@ def prepare(tmp):
     with open(os.path.join(dat, 'mpileup.bam.list'), 'w') as o:
         for n in (1, 2, 3):
             o.write(os.path.join(dat, f'mpileup.{n}.sam') + '\n')
+    # BASELINE config 1: examples/ex1.sam.gz is headerless; `samtools view -t ex1.fa.fai` is replaced by the
+    # readers taking the contig list from <ref>.fai, which `samtools faidx` would have written
+    ex = os.path.join(root, 'examples')
+    rows, name, ln, lb, lw, start, off = [], None, 0, 0, 0, 0, 0
+    for line in open(os.path.join(ex, 'ex1.fa'), 'rb'):
+        if line.startswith(b'>'):
+            if name:
+                rows.append((name, ln, start, lb, lw))
+            name, ln, lb, lw, start = line[1:].split()[0].decode(), 0, 0, 0, off + len(line)
+        else:
+            if lb == 0:
+                lb, lw = len(line.rstrip(b'\n')), len(line)
+            ln += len(line.rstrip(b'\n'))
+        off += len(line)
+    rows.append((name, ln, start, lb, lw))
+    with open(os.path.join(ex, 'ex1.fa.fai'), 'w') as o:
+        o.write(''.join('%s\t%d\t%d\t%d\t%d\n' % r for r in rows))
     return root
+
+
+EX1_CMDS = ['mpileup -f ex1.fa ex1.sam.gz', 'mpileup -B -f ex1.fa ex1.sam.gz', 'mpileup -a -x -Q 20 -q 30 -f ex1.fa ex1.sam.gz',
+            'mpileup -B -aa -s -O -f ex1.fa -r seq2:100-600 ex1.sam.gz']
 
 
 def all_cases():

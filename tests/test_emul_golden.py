@@ -31,3 +31,12 @@ def test_host_drivers_and_column_code(case, emul_bin, oracle_bin, corpus):
     if not ok and b'not available on the device path' in err:
         pytest.skip('--output-extra/QNAME/mods: host-string columns not on the device path yet')
     assert ok, f"{case['cmd']}\nstderr: {err[-300:]!r}\nstdout head: {out[:200]!r}"
+
+
+@pytest.mark.parametrize('cmd', [c for c in golden_cases.EX1_CMDS if ' -B ' in c])
+def test_c1_ex1_host_path(cmd, emul_bin, oracle_bin, corpus):
+    """BASELINE config 1 plumbing (headerless SAM + .fai contig list) through the host drivers, no GPU."""
+    cwd = os.path.join(corpus, 'examples')
+    want = subprocess.run(f'{oracle_bin} {cmd}', shell=True, cwd=cwd, capture_output=True)
+    got = subprocess.run(f'{emul_bin} {cmd}', shell=True, cwd=cwd, capture_output=True)
+    assert len(want.stdout) > 1000 and got.stdout == want.stdout

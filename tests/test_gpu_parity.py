@@ -180,3 +180,14 @@ def test_htslib_compat_iterator(args, files, oracle_bin, corpus):
     assert got.returncode == 0, got.stderr[-300:]
     assert got.stdout == want.stdout
     assert len(got.stdout) > 100
+
+
+# ---------------------------------------------------------------- BASELINE config 1 (examples/ex1): engine vs oracle
+@pytest.mark.parametrize('cmd', golden_cases.EX1_CMDS)
+def test_c1_ex1_engine_vs_oracle(cmd, cli, oracle_bin, corpus):
+    """No expected output exists in-tree for examples/ex1: parity is oracle vs engine."""
+    cwd = os.path.join(corpus, 'examples')
+    want = subprocess.run(f'{oracle_bin} {cmd}', shell=True, cwd=cwd, capture_output=True)
+    got = subprocess.run(f'{cli} {cmd}', shell=True, cwd=cwd, capture_output=True)
+    assert got.returncode == 0 and len(want.stdout) > 1000
+    assert got.stdout == want.stdout
