@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(TILE, 12) k_mpileup_write_occ(MpFmt fmt, const
 
 #include "mpileup_rm.cuh"
 #include "mpileup_w4.cuh"
+#include "mpileup_ss.cuh"
 
 // depth rows "name\tpos(\tdepth)*\n" (bam2depth.c:234-244)
 struct DpFmt {
@@ -604,6 +605,7 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
     s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
     s = getenv("B200_PLP_WRITE_OCC"); e->write_occ = s ? atoi(s) : 0;
+    s = getenv("B200_PLP_STREAM_SIZE"); e->stream_size = s ? atoi(s) : 1;
     cudaFuncSetAttribute(k_mpileup_write_occ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + one-column-per-thread write (default), 1: column-major both, 2: read-major both, 4: read-major sizing + 4-columns-per-thread write
     if (e->chained) e->variant = 1;
@@ -936,7 +938,24 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
     CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
     CK(cudaEventRecord(e->ev0, e->stream));
-    k_mp_rm_size<<<ntr, RM_WARPS * 32, 0, e->stream>>>(fmt.v, fmt.cf, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
+    if (e->stream_size && e->variant == 0 && e->n_files == 1 && !c->out_qpos && !c->out_qpos5) {
+        // order-free streaming size pass (mpileup_ss.cuh)
+        ENSURE(ss_diff, (size_t)ncols + 2); ENSURE(ss_nplp, (size_t)ncols + 2); ENSURE(ss_fail, (size_t)ncols + 1); ENSURE(ss_extra, (size_t)ncols + 1);
+        CK(cudaMemsetAsync(e->ss_diff, 0, ((size_t)ncols + 2) * 4, e->stream));
+        CK(cudaMemsetAsync(e->ss_fail, 0, ((size_t)ncols + 1) * 4, e->stream));
+        CK(cudaMemsetAsync(e->ss_extra, 0, ((size_t)ncols + 1) * 4, e->stream));
+        const int nbs = nblk((int64_t)ncols + 1, 1024);
+        ENSURE(status2, (size_t)nbs + 1);
+        CK(cudaMemsetAsync(e->status2, 0, ((size_t)nbs + 1) * 8, e->stream));
+        CK(cudaMemsetAsync(e->d_misc + 2, 0, 8, e->stream));
+        const int64_t want_blocks = (e->n * 32 + 255) / 256;
+        const int rb = (int)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)e->n_sm * 16));
+        k_ss_reads<<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, e->ss_diff, e->ss_fail, e->ss_extra); e->launches++;
+        k_ss_scan<<<nbs, 256, 0, e->stream>>>(e->ss_diff, e->ss_nplp, ncols + 1, e->status2, (uint32_t *)(e->d_misc + 2)); e->launches++;
+        k_ss_cols<<<nt, TILE, 0, e->stream>>>(fmt.v, fmt.cf, e->ss_nplp, e->ss_fail, e->ss_extra, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
+    } else {
+        k_mp_rm_size<<<ntr, RM_WARPS * 32, 0, e->stream>>>(fmt.v, fmt.cf, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
+    }
     CK(cudaEventRecord(e->evA, e->stream));
     k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
     CK(cudaEventRecord(e->evB, e->stream));

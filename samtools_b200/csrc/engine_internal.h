@@ -18,7 +18,7 @@ struct b200_engine {
     int64_t launches = 0;
     double last_kernel_ms = 0, last_stage_ms = 0;
     uint32_t smem_text = 24 * 1024;
-    int use_tma = 1, chained = 0, variant = 0, write_occ = 0;
+    int use_tma = 1, chained = 0, variant = 0, write_occ = 0, stream_size = 1;
     uint32_t smem_text_rm = 36 * 1024;
 
     // raw SoA image of the staged records
@@ -32,7 +32,8 @@ struct b200_engine {
     DBUF(int32_t, glo); DBUF(int32_t, ghi); DBUF(uint64_t, status); DBUF(char, out);
     DBUF(int64_t, bed_beg); DBUF(int64_t, bed_end);
     DBUF(uint32_t, col_n); DBUF(uint64_t, col_off); DBUF(uint64_t, col_state); DBUF(uint32_t, tile_total);
-    DBUF(uint32_t, ovf_cnt); DBUF(int32_t, ovf_off); DBUF(int32_t, ovf_idx); DBUF(b200_pileup1_t, ents);
+    DBUF(uint32_t, ovf_cnt); DBUF(int32_t, ovf_off); DBUF(int32_t, ovf_idx);
+    DBUF(int32_t, ss_diff); DBUF(int32_t, ss_nplp); DBUF(uint32_t, ss_fail); DBUF(uint32_t, ss_extra); DBUF(uint64_t, status2); DBUF(b200_pileup1_t, ents);
     DBUF(int32_t, clip); DBUF(int64_t, next); DBUF(int32_t, cig_x); DBUF(int32_t, cig_y);
     DBUF(double, baq_f); DBUF(int32_t, baq_idx);
     DBUF(float, gl_out); DBUF(int32_t, gl_n); DBUF(uint32_t, gl_flag);
@@ -64,7 +65,7 @@ struct b200_engine {
     {
         void *ps[] = { pos, flag, mapq, l_qseq, n_cigar, cigar_off, qual_off, mtid, mpos, isize, prev, rbits, cigar, seq4, qual,
                        ref, dname, file_start, state, rlen, desc, endv, pmax, glo, ghi, status, out, bed_beg, bed_end, col_n,
-                       col_off, col_state, tile_total, ovf_cnt, ovf_off, ovf_idx, ents, clip, next, cig_x, cig_y, baq_f, baq_idx, gl_out, gl_n, gl_flag, d_beta, d_fk, d_lhet, d_q2p, d_qthr };
+                       col_off, col_state, tile_total, ovf_cnt, ovf_off, ovf_idx, ss_diff, ss_nplp, ss_fail, ss_extra, status2, ents, clip, next, cig_x, cig_y, baq_f, baq_idx, gl_out, gl_n, gl_flag, d_beta, d_fk, d_lhet, d_q2p, d_qthr };
         for (void *p : ps) if (p) cudaFree(p);
     }
 };

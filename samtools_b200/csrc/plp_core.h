@@ -493,14 +493,26 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
         }
         const bool ends = !cf.no_ends, extras = (cf.out_mapq | cf.out_qpos | cf.out_qpos5) != 0;
         const int minq = cf.min_baseQ;
-        auto body = [&](ReadDesc d, int32_t i) {
+        // operands of a simple read's entry, fetched one iteration ahead of their use
+        struct Pre { int q; uint32_t sb; };
+        auto prefetch = [&](const ReadDesc &d) -> Pre {
+            Pre o; o.q = 0; o.sb = 0;
+            const uint32_t rel = (uint32_t)(c - d.rpos);
+            if (rel < (uint32_t)(d.rend - d.rpos) && (d.fl & RD_SIMPLE)) {
+                const uint32_t qi = d.qoff + (uint32_t)d.qstart + rel;
+                o.q = (int)v.qual[qi];
+                o.sb = v.seq4[qi >> 1];
+            }
+            return o;
+        };
+        auto body = [&](ReadDesc d, int32_t i, const Pre &pre) {
             const uint32_t rel = (uint32_t)(c - d.rpos);
             if (rel >= (uint32_t)(d.rend - d.rpos)) return;
             int q, qpos1 = 0; int32_t q5 = 0;
             if (d.fl & RD_SIMPLE) {
                 const uint32_t qi = d.qoff + (uint32_t)d.qstart + rel;
-                q = (int)v.qual[qi];
-                const uint8_t sb = v.seq4[qi >> 1];          // issued together with the quality load
+                q = pre.q;
+                const uint32_t sb = pre.sb;
                 if (q < minq) return;
                 const bool rev = d.fl & RD_REV;
                 if (ends && rel == 0) { *ps++ = '^'; *ps++ = (char)(d.mapq > 93 ? 126 : d.mapq + 33); }
@@ -531,14 +543,20 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
                 ++n;
             }
         };
-        for (int32_t t_ = 0; t_ < rr.n_ovf; ++t_) { const int32_t i = rr.ovf[t_]; body(load_hot(v.desc + i), i); }
+        for (int32_t t_ = 0; t_ < rr.n_ovf; ++t_) { const int32_t i = rr.ovf[t_]; const ReadDesc d = load_hot(v.desc + i); body(d, i, prefetch(d)); }
         const int32_t hi_ = rr.lo + (rr.n - rr.n_ovf);
         if (rr.lo < hi_) {
-            ReadDesc dn = load_hot(v.desc + rr.lo);             // software pipelining: fetch descriptor i+1 while i is formatted
+            // two-deep software pipeline: while entry i is formatted, the quality/base bytes of read i+1 and the
+            // descriptor of read i+2 are in flight (the loop is bound by dependent-load latency otherwise)
+            ReadDesc d0 = load_hot(v.desc + rr.lo);
+            ReadDesc d1 = rr.lo + 1 < hi_ ? load_hot(v.desc + rr.lo + 1) : d0;
+            Pre p0 = prefetch(d0);
             for (int32_t i = rr.lo; i < hi_; ++i) {
-                const ReadDesc d = dn;
-                if (i + 1 < hi_) dn = load_hot(v.desc + i + 1);
-                body(d, i);
+                const ReadDesc d = d0; const Pre pr = p0;
+                d0 = d1;
+                if (i + 1 < hi_) p0 = prefetch(d0);
+                if (i + 2 < hi_) d1 = load_hot(v.desc + i + 2);
+                body(d, i, pr);
             }
         }
     }
