@@ -119,10 +119,29 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_s
 
 // ============================== read stage ===================================
 // (arithmetic in plp_stage.h; one thread per read)
+__device__ __forceinline__ void merge_acc(const StageAcc &a, StageAcc *g)
+{
+    unsigned long long v[7] = {a.n_kept, a.n_kept_in_window, a.sum_rlen, a.sum_indel_text, a.n_reads, a.n_selected, a.summed_mapq};
+    int mx = a.max_rend;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long *gp[7] = {&g->n_kept, &g->n_kept_in_window, &g->sum_rlen, &g->sum_indel_text, &g->n_reads, &g->n_selected, &g->summed_mapq};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) if (v[k]) atomicAdd(gp[k], v[k]);
+        if (mx != INT32_MIN) atomicMax(&g->max_rend, mx);
+    }
+}
 __global__ void k_prep1(RawSoA r, b200_stage_conf_t cf, uint8_t *state, int32_t *rlen_out, StageAcc *acc)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < r.n) stage_prep1(r, cf, i, state, rlen_out, acc);
+    StageAcc loc; memset(&loc, 0, sizeof loc); loc.max_rend = INT32_MIN;
+    if (i < r.n) stage_prep1(r, cf, i, state, rlen_out, &loc);
+    if (cf.mode == B200_MODE_COVERAGE) merge_acc(loc, acc);
 }
 __global__ void k_prep2(RawSoA r, b200_stage_conf_t cf, uint8_t *state)
 {
@@ -133,7 +152,9 @@ __global__ void k_build_desc(RawSoA r, b200_stage_conf_t cf, const uint8_t *stat
                              ReadDesc *desc, int32_t *endv, StageAcc *acc, int64_t win_base, int32_t *cig_x, int32_t *cig_y)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < r.n) stage_build_desc(r, cf, i, state, rlen, desc, endv, acc, win_base, cig_x, cig_y);
+    StageAcc loc; memset(&loc, 0, sizeof loc); loc.max_rend = INT32_MIN;
+    if (i < r.n) stage_build_desc(r, cf, i, state, rlen, desc, endv, &loc, win_base, cig_x, cig_y);
+    merge_acc(loc, acc);
 }
 
 // inclusive prefix max of endv[] (single pass, decoupled look-back, one file at a time)

@@ -26,12 +26,19 @@ __global__ void __launch_bounds__(256) k_ss_reads(View v, MpConf cf, int64_t n_r
         if (lane == 0) { atomicAdd(&diff[a], 1); atomicAdd(&diff[b], -1); }
         if (d.fl & RD_SIMPLE) {
             const uint32_t qbase = d.qoff + (uint32_t)d.qstart - (uint32_t)d.rpos;
-            for (int32_t c = a + lane; c < b; c += 32) {
-                const int q = (int)v.qual[qbase + (uint32_t)c];
-                if (q < cf.min_baseQ) atomicAdd(&fail[c], 1u);
-                else {
-                    const uint32_t x = (ends & (uint32_t)(c == d.rpos)) * 2u + (ends & (uint32_t)(c == d.rend - 1));
-                    if (x) atomicAdd(&extra[c], x);
+            for (int32_t c0 = a + lane; c0 < b; c0 += 32 * 8) {       // eight independent loads in flight per lane
+                int q[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const int32_t c = c0 + 32 * k; q[k] = c < b ? (int)v.qual[qbase + (uint32_t)c] : 255; }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int32_t c = c0 + 32 * k;
+                    if (c >= b) break;
+                    if (q[k] < cf.min_baseQ) atomicAdd(&fail[c], 1u);
+                    else {
+                        const uint32_t x = (ends & (uint32_t)(c == d.rpos)) * 2u + (ends & (uint32_t)(c == d.rend - 1));
+                        if (x) atomicAdd(&extra[c], x);
+                    }
                 }
             }
         } else {
