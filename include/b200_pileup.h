@@ -68,6 +68,10 @@ typedef struct {
     const int64_t *prev_same_name; /* [n_reads], may be NULL if unused */
     /* per read host bits, see B200_RB_* */
     const uint8_t *rbits;        /* [n_reads], may be NULL (= all zero) */
+    /* depth -s only: absolute clip coordinate of each read (0 = none), when the caller has replayed the
+     * reference's name hash itself (bam2depth.c:598-623 keeps ONE hash per file across reference sequences, so a
+     * name seen on an earlier contig can clip a read here); NULL = the device derives it from prev_same_name */
+    const int64_t *depth_clip;   /* [n_reads], may be NULL */
     /* packed payload */
     const uint32_t *cigar;  uint64_t n_cigar_total;   /* BAM encoding len<<4|op */
     const uint8_t *seq4;    /* 4-bit bases, (qual_bytes+1)/2 bytes */

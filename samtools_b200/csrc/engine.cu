@@ -793,7 +793,19 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
             }
         }
         if (cf->mode == B200_MODE_MPILEUP && cf->overlaps && e->has_prev) { if (launch_overlap(e, r)) return -1; }
-        if (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps && e->has_prev) { if (launch_depth_clip(e, r)) return -1; }
+        if (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps && b->depth_clip) {
+            // clip coordinates replayed by the caller (one name hash per file, across reference sequences)
+            e->h_clip_tmp.resize((size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                const int64_t cabs = b->depth_clip[i];
+                int64_t rel = cabs ? cabs - e->win_base : (int64_t)INT32_MIN;
+                if (rel > INT32_MAX) rel = INT32_MAX;
+                if (rel < INT32_MIN) rel = INT32_MIN;
+                e->h_clip_tmp[(size_t)i] = (int32_t)rel;
+            }
+            H2D(clip, e->h_clip_tmp.data(), n);
+            e->has_clip = true;
+        } else if (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps && e->has_prev) { if (launch_depth_clip(e, r)) return -1; }
         else e->has_clip = false;
     } else {
         CK(cudaMemsetAsync(e->glo, 0, ((size_t)e->n_groups * e->n_files) * 4, e->stream));

@@ -54,7 +54,7 @@ struct b200_engine {
     size_t last_out_len = 0;
     uint64_t gl_rng_draws = 0;   // hts_drand48 draws consumed so far by errmod's ks_shuffle
     std::vector<int64_t> h_file_start;
-    std::vector<int32_t> h_rlen_tmp;
+    std::vector<int32_t> h_rlen_tmp, h_clip_tmp;
 
     uint64_t text_bound(int per_entry, int per_file_extra) const
     {

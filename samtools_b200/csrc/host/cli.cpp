@@ -22,6 +22,7 @@
 #include <cerrno>
 #include <algorithm>
 #include <set>
+#include <unordered_map>
 
 using namespace b200;
 
@@ -386,12 +387,53 @@ int main_depth(int argc, char **argv)
     b200_depth_conf_t dc; memset(&dc, 0, sizeof dc);
     dc.min_qual = min_qual; dc.count_del = !skip_del; dc.all = all_pos;
     PackedBatch pb; std::vector<char> out; std::vector<int64_t> bb, be;
+    // depth -s: the reference keeps one qname -> end-position hash PER FILE for the whole run (bam2depth.c:598-623),
+    // i.e. across reference sequences, and only records that pass the read filters take part.  It is replayed here
+    // in file order (name hashing is host work anyway) and handed to the engine as one clip coordinate per record.
+    std::vector<std::vector<std::vector<int64_t>>> clips((size_t)nfn);
+    if (remove_overlaps) {
+        auto qlen_used = [](const Record &r) -> int64_t {
+            int64_t l;
+            const int n = (int)r.cigar.size();
+            if (r.l_qseq) {
+                l = r.l_qseq; int kl, kr;
+                for (kl = 0; kl < n; kl++) { if ((r.cigar[(size_t)kl] & 0xf) == 4) l -= r.cigar[(size_t)kl] >> 4; else break; }
+                for (kr = n - 1; kr > kl; kr--) { if ((r.cigar[(size_t)kr] & 0xf) == 4) l -= r.cigar[(size_t)kr] >> 4; else break; }
+            } else { l = 0; for (uint32_t c : r.cigar) { int op = c & 0xf; if (op == 0 || op == 1 || op == 7 || op == 8) l += c >> 4; } }
+            return l;
+        };
+        for (int i = 0; i < nfn; ++i) {
+            std::unordered_map<std::string, int64_t> seen;
+            clips[(size_t)i].resize(fd[(size_t)i].by_tid.size());
+            for (size_t t = 0; t < fd[(size_t)i].by_tid.size(); ++t) {
+                auto &cv = clips[(size_t)i][t];
+                for (const Record &r : fd[(size_t)i].by_tid[t]) {
+                    int64_t clip = 0;
+                    const bool pass = !(r.flag & flag) && !(incl && (r.flag & incl) == 0) && (r.flag & require) == require &&
+                                      r.mapq >= min_mqual && !(min_len && qlen_used(r) < min_len);
+                    if (pass && (r.flag & F_PAIRED) && !(r.flag & F_MUNMAP)) {
+                        auto it = seen.find(r.qname);
+                        if (it == seen.end()) { const int64_t e = r.endpos(); if (r.mpos == -1 || (r.tid == r.mtid && r.mpos <= e)) seen.emplace(r.qname, e); }
+                        else { clip = it->second; seen.erase(it); }
+                    }
+                    cv.push_back(clip);
+                }
+            }
+        }
+    }
     auto process_tid = [&](int tid, bool with_reads) -> int {
         const std::string &name = h.names[(size_t)tid];
         pb.clear();
         for (int i = 0; i < nfn; ++i) {
             pb.begin_file();
-            if (with_reads && tid < (int)fd[(size_t)i].by_tid.size()) for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) pb.add(r, 0, remove_overlaps != 0);
+            if (with_reads && tid < (int)fd[(size_t)i].by_tid.size()) {
+                size_t k = 0;
+                for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) {
+                    pb.add(r, 0, false);
+                    if (remove_overlaps) pb.depth_clip.push_back(clips[(size_t)i][(size_t)tid][k]);
+                    ++k;
+                }
+            }
         }
         pb.finish();
         b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], name, nullptr);

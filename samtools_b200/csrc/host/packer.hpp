@@ -13,7 +13,7 @@
 namespace b200 {
 
 struct PackedBatch {
-    std::vector<int64_t> file_start, pos, mpos, isize, prev;
+    std::vector<int64_t> file_start, pos, mpos, isize, prev, depth_clip;
     std::vector<uint16_t> flag;
     std::vector<uint8_t> mapq, rbits, seq4, qual;
     std::vector<int32_t> l_qseq, mtid;
@@ -25,6 +25,7 @@ struct PackedBatch {
     {
         file_start.clear(); pos.clear(); mpos.clear(); isize.clear(); prev.clear(); flag.clear(); mapq.clear(); rbits.clear();
         seq4.clear(); qual.clear(); l_qseq.clear(); mtid.clear(); n_cigar.clear(); cigar.clear(); cigar_off.clear(); qual_off.clear();
+        depth_clip.clear();
     }
     void begin_file() { file_start.push_back((int64_t)pos.size()); names_.clear(); }
     void finish() { file_start.push_back((int64_t)pos.size()); if (seq4.size() * 2 < qual.size() + 2) seq4.resize((qual.size() + 2) / 2, 0); }
@@ -65,6 +66,7 @@ struct PackedBatch {
         b.pos = pos.data(); b.flag = flag.data(); b.mapq = mapq.data(); b.l_qseq = l_qseq.data(); b.n_cigar = n_cigar.data();
         b.cigar_off = cigar_off.data(); b.qual_off = qual_off.data(); b.mtid = mtid.data(); b.mpos = mpos.data(); b.isize = isize.data();
         b.prev_same_name = prev.data(); b.rbits = rbits.data();
+        b.depth_clip = depth_clip.size() == pos.size() && !pos.empty() ? depth_clip.data() : nullptr;
         b.cigar = cigar.data(); b.n_cigar_total = cigar.size(); b.seq4 = seq4.data(); b.qual = qual.data(); b.qual_bytes = qual.size();
         b.tid = tid; b.tid_len = tid_len; b.tid_name = tid_name.c_str();
         b.ref = ref ? ref->data() : nullptr; b.ref_beg = 0; b.ref_n = ref ? (int64_t)ref->size() : 0; b.ref_len = ref ? (int64_t)ref->size() : 0;

@@ -26,7 +26,7 @@ class Batch(C.Structure):
     _fields_ = [('n_files', C.c_int32), ('n_reads', C.c_int64), ('file_start', C.c_void_p),
                 ('pos', C.c_void_p), ('flag', C.c_void_p), ('mapq', C.c_void_p), ('l_qseq', C.c_void_p),
                 ('n_cigar', C.c_void_p), ('cigar_off', C.c_void_p), ('qual_off', C.c_void_p), ('mtid', C.c_void_p),
-                ('mpos', C.c_void_p), ('isize', C.c_void_p), ('prev_same_name', C.c_void_p), ('rbits', C.c_void_p),
+                ('mpos', C.c_void_p), ('isize', C.c_void_p), ('prev_same_name', C.c_void_p), ('rbits', C.c_void_p), ('depth_clip', C.c_void_p),
                 ('cigar', C.c_void_p), ('n_cigar_total', C.c_uint64), ('seq4', C.c_void_p), ('qual', C.c_void_p),
                 ('qual_bytes', C.c_uint64), ('tid', C.c_int32), ('tid_len', C.c_int64), ('tid_name', C.c_char_p),
                 ('ref', C.c_void_p), ('ref_beg', C.c_int64), ('ref_n', C.c_int64), ('ref_len', C.c_int64)]
@@ -151,7 +151,7 @@ class Engine:
         b.n_files = len(soa['file_start']) - 1
         b.n_reads = len(soa['pos'])
         for k in ('file_start', 'pos', 'flag', 'mapq', 'l_qseq', 'n_cigar', 'cigar_off', 'qual_off', 'mtid', 'mpos', 'isize',
-                  'prev_same_name', 'rbits', 'cigar', 'seq4', 'qual'):
+                  'prev_same_name', 'rbits', 'depth_clip', 'cigar', 'seq4', 'qual'):
             setattr(b, k, _ptr(soa.get(k)))
         b.n_cigar_total = len(soa['cigar'])
         b.qual_bytes = len(soa['qual'])

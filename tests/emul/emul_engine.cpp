@@ -149,7 +149,16 @@ int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t 
         }
     }
     e->has_clip = false;
-    if (b->prev_same_name && ((cf->mode == B200_MODE_MPILEUP && cf->overlaps) || (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps))) {
+    if (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps && b->depth_clip) {
+        e->clip.assign((size_t)n + 1, INT32_MIN);
+        for (int64_t i = 0; i < n; ++i) {
+            int64_t rel = b->depth_clip[i] ? b->depth_clip[i] - e->win_base : (int64_t)INT32_MIN;
+            if (rel > INT32_MAX) rel = INT32_MAX;
+            if (rel < INT32_MIN) rel = INT32_MIN;
+            e->clip[(size_t)i] = (int32_t)rel;
+        }
+        e->has_clip = true;
+    } else if (b->prev_same_name && ((cf->mode == B200_MODE_MPILEUP && cf->overlaps) || (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps))) {
         e->next.assign((size_t)n + 1, -1);
         for (int64_t i = 0; i < n; ++i) if (b->prev_same_name[i] >= 0) e->next[(size_t)b->prev_same_name[i]] = i;
         if (cf->mode == B200_MODE_MPILEUP) {
