@@ -10,16 +10,20 @@
 //   derived     ReadDesc[32 B] per read, prefix-max of read ends, per-32-column
 //               [lo,hi) read ranges, look-back status words, output text
 //
-// Column stage = one thread per reference position.  A CTA owns 128 adjacent
-// columns: (1) every thread sizes its output line by walking the reads whose
-// range covers its warp's 32 columns, (2) a block scan + decoupled look-back
-// across CTAs (ticket-ordered, single pass) gives the CTA its byte offset in
-// the output, (3) the lines are formatted into shared memory laid out with the
-// same 16-byte phase as the destination and (4) leave the SM as one
-// cp.async.bulk (TMA) shared->global store plus <16 B ragged edges.
-// HBM traffic per column is therefore ~ the algorithmic bytes: reads are
-// fetched once through L1/L2 (neighbouring columns share them), text is
-// written once, fully coalesced.  No tensor cores: integer/byte work.
+// Column stage for text (mpileup, depth): sizes -> offsets -> bytes, no inter-CTA waiting.
+//   (1) a size pass gives every column its line length (mpileup: order-free streaming pass
+//       over the reads, mpileup_ss.cuh; depth: thread per column);
+//   (2) a single-pass scan of 128-column tile totals gives every tile its byte offset;
+//   (3) the write pass: one thread per reference position walks the reads whose slice covers
+//       its 32-column group (descriptors and quality/base bytes software-pipelined), formats
+//       its line into shared memory laid out with the destination's 16-byte phase, and the
+//       tile leaves the SM as one cp.async.bulk (TMA) shared->global store plus <16 B edges.
+// HBM traffic per column is ~ the algorithmic bytes: reads are fetched once per pass through
+// L1/L2 (neighbouring columns share them), text is written once, fully coalesced.
+// Selectable variants kept for A/B and as mutual cross-checks (tests require identical bytes):
+// read-major sizing / write (mpileup_rm.cuh), 4 columns per thread (mpileup_w4.cuh), and the
+// first design, a single chained launch with decoupled look-back (k_mpileup).
+// No tensor cores: integer/byte work.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
