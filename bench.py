@@ -303,7 +303,7 @@ def main():
                 'roofline': {'bound': 'hbm', 'kernel': 'k_mpileup_write', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(alg),
                              'bytes_in': int(bytes_in), 'bytes_out': int(out_len), 'kernel_ms': write_ms,
-                             'step_kernels_ms': {'k_mp_rm_size': size_ms, 'k_scan_u32_to_u64': scan_ms, 'k_mpileup_write': write_ms, 'total': kms},
+                             'step_kernels_ms': {'size_pass(k_ss_reads+k_ss_scan+k_ss_cols)': size_ms, 'k_scan_u32_to_u64': scan_ms, 'k_mpileup_write': write_ms, 'total': kms},
                              'step_frac': alg / (kms * 1e-3) / 1e9 / peak},
                 'reads_per_step_per_gpu': n_reads}
         if world == 1 and not args.no_cpu_baseline:

@@ -267,6 +267,12 @@ __global__ void k_ovf_fill(const ReadDesc *desc, const int64_t *file_start, int 
         idx[off[k] + (int32_t)atomicAdd(&cursor[k], 1u)] = (int32_t)i;
     }
 }
+// longest far-reaching list (enters the "can a column exceed the depth cap" bound next to the widest slice)
+__global__ void k_ovf_max(const uint32_t *cnt, int64_t n_lists, int *out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_lists && cnt[k]) atomicMax(out, (int)cnt[k]);
+}
 __global__ void k_ovf_sort(const int32_t *off, int32_t *idx, int64_t n_lists)   // lists are tiny: insertion sort restores file order
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,6 +442,7 @@ __global__ void __launch_bounds__(TILE, 12) k_mpileup_write_occ(MpFmt fmt, const
 #include "mpileup_rm.cuh"
 #include "mpileup_w4.cuh"
 #include "mpileup_ss.cuh"
+#include "mpileup_sr.cuh"
 
 // depth rows "name\tpos(\tdepth)*\n" (bam2depth.c:234-244)
 struct DpFmt {
@@ -631,6 +638,8 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
     s = getenv("B200_PLP_WRITE_OCC"); e->write_occ = s ? atoi(s) : 0;
     s = getenv("B200_PLP_STREAM_SIZE"); e->stream_size = s ? atoi(s) : 1;
+    s = getenv("B200_PLP_SR"); e->sr_write = s ? atoi(s) : 0;
+    cudaFuncSetAttribute(k_mp_sr_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_mpileup_write_occ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + one-column-per-thread write (default), 1: column-major both, 2: read-major both, 4: read-major sizing + 4-columns-per-thread write
     if (e->chained) e->variant = 1;
@@ -852,6 +861,7 @@ int build_ranges(b200_engine *e, int *max_range)
     ENSURE(ovf_cnt, (size_t)tot + 1); ENSURE(ovf_off, (size_t)tot + 2);
     CK(cudaMemsetAsync(e->ovf_cnt, 0, ((size_t)tot + 1) * 4, e->stream));
     k_ovf_count<<<nblk(n, 256), 256, 0, e->stream>>>(e->desc, e->file_start, e->n_files, n, e->n_groups, e->ovf_cnt); e->launches++;
+    k_ovf_max<<<nblk(tot, 256), 256, 0, e->stream>>>(e->ovf_cnt, tot, (int *)(e->d_misc + 1) + 1); e->launches++;
     {
         const int nb = nblk(tot, 256);
         ENSURE(status, (size_t)nb + 1);
@@ -861,8 +871,10 @@ int build_ranges(b200_engine *e, int *max_range)
     }
     int32_t n_ovf = 0;
     CK(cudaMemcpyAsync(&n_ovf, e->ovf_off + tot, 4, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(max_range, e->d_misc + 1, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    int mx[2] = {0, 0};                        // widest slice, longest far-reaching list
+    CK(cudaMemcpyAsync(mx, e->d_misc + 1, sizeof mx, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    *max_range = mx[0] + mx[1];                // no column holds more reads than this
     ENSURE(ovf_idx, (size_t)n_ovf + 1);
     if (n_ovf > 0) {
         CK(cudaMemsetAsync(e->ovf_cnt, 0, ((size_t)tot + 1) * 4, e->stream));
@@ -1006,7 +1018,9 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
                                                                               e->smem_text_rm, e->use_tma);
     } else {
         const int ntw = (ncols + TILE - 1) / TILE;
-        if (e->write_occ) k_mpileup_write_occ<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        if (e->sr_write && e->variant == 0 && e->n_files == 1 && !c->out_qpos && !c->out_qpos5)
+            k_mp_sr_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        else if (e->write_occ) k_mpileup_write_occ<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
         else k_mpileup_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
     }
     e->launches++;

@@ -18,7 +18,7 @@ struct b200_engine {
     int64_t launches = 0;
     double last_kernel_ms = 0, last_stage_ms = 0;
     uint32_t smem_text = 24 * 1024;
-    int use_tma = 1, chained = 0, variant = 0, write_occ = 0, stream_size = 1;
+    int use_tma = 1, chained = 0, variant = 0, write_occ = 0, stream_size = 1, sr_write = 0;
     uint32_t smem_text_rm = 36 * 1024;
 
     // raw SoA image of the staged records

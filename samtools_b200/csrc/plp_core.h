@@ -609,6 +609,130 @@ PLP_HD void mp_line_write(const View &v, const MpConf &cf, int tile, int32_t c, 
     *p = '\n';
 }
 
+// ---- building blocks of the staged-reads write pass (mpileup_sr.cuh) ---------------------
+// A CTA first copies, for every read over its 128 columns, just the quality bytes and base
+// nibbles that fall inside the tile into shared memory (warp per read, aligned word loads, no
+// per-base work) together with one 32-bit word describing the read relative to the tile; then
+// every thread walks ITS column down the slots with shared-memory loads only.
+//
+// slot word: bits 0-7  first covered column (tile-local)      8-15 number of covered columns (0: none)
+//            16-17 byte offset of that column in the staged quality row
+//            18-20 nibble offset of that column in the staged base row
+//            24 reverse strand   25 simple [S]<n>M[S] read (staged)   26 "^"+mapq at the first covered column
+//            27 "$" at the last covered column
+// An entry leaves sr_entry as: 0 = nothing to print (base fails -Q), else bits 0-6 base
+// character, bit 7 "^"+mapq first, bits 8-14 quality character, bit 15 "$" after.
+constexpr uint32_t SR_SIMPLE = 1u << 25;
+constexpr int SR_COLS = 128;          // columns per tile
+constexpr int SR_QROW = 33;           // staged quality row, words: <= 3 + 128 bytes
+constexpr int SR_SROW = 18;           // staged base row, words: <= 7 + 128 nibbles
+
+PLP_HD uint32_t umin32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return min(a, b);
+#else
+    return a < b ? a : b;
+#endif
+}
+
+// slot word of read d (first half of the descriptor) for the tile starting at column c0;
+// qi_a = query index (quality byte / base nibble) of the first covered column, simple reads only
+PLP_HD uint32_t sr_meta(const ReadDesc &d, int32_t c0, uint32_t ends, uint32_t &qi_a)
+{
+    const int32_t a = d.rpos > c0 ? d.rpos : c0, b = d.rend < c0 + SR_COLS ? d.rend : c0 + SR_COLS;
+    qi_a = 0;
+    if (a >= b) return 0;
+    uint32_t m = (uint32_t)(a - c0) | (uint32_t)(b - a) << 8;
+    if (d.fl & RD_SIMPLE) {
+        qi_a = d.qoff + (uint32_t)d.qstart + (uint32_t)(a - d.rpos);
+        m |= (qi_a & 3u) << 16 | (qi_a & 7u) << 18 | SR_SIMPLE;
+    }
+    m |= (uint32_t)((d.fl & RD_REV) != 0) << 24 | (ends & (uint32_t)(a == d.rpos)) << 26 | (ends & (uint32_t)(b == d.rend)) << 27;
+    return m;
+}
+
+// entry of a staged read at its r-th covered column: q = quality byte, sbyte = the staged byte
+// holding base nibble nib (= nibble offset + r), rb = reference code of the column (0x10: no FASTA),
+// tab = ".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn" (forward strand, then reverse)
+PLP_HD uint32_t sr_entry(uint32_t m, uint32_t r, uint32_t q, uint32_t sbyte, uint32_t nib, uint32_t rb, int minq, const uint8_t *tab)
+{
+    if ((int)q < minq) return 0;
+    uint32_t code = (sbyte >> ((~nib & 1u) << 2)) & 0xfu;
+    if (code == rb) code = 0;
+    uint32_t x = (uint32_t)tab[((m >> 20) & 0x10u) | code] | umin32(q + 33u, 126u) << 8;
+    x |= ((m >> 26) & (uint32_t)(r == 0)) << 7 | ((m >> 27) & (uint32_t)(r + 1u == ((m >> 8) & 0xffu))) << 15;
+    return x;
+}
+
+// reference code of column c as pileup_seq compares it (bam_plcmd.c:74-80); 0x10 without a FASTA
+PLP_HD uint32_t sr_ref_code(const View &v, int32_t c)
+{
+    if (!v.ref) return 0x10u;
+    if ((int64_t)c < v.ref_len_rel) { const int64_t ri = (int64_t)c - v.ref_off; if (ri >= 0 && ri < v.ref_n) return (uint32_t)nt16_of((unsigned char)v.ref[ri]); }
+    return 15u;
+}
+
+// Everything of a single-file line except the entries: header, count, separators, "*" place
+// holders, newline.  Returns the cursors the entries are appended through (ps == nullptr: none).
+struct SrCur { char *ps, *pq, *pm; };
+PLP_HD SrCur sr_layout(const View &v, const MpConf &cf, int32_t c, const MpFileSz &s, char *p)
+{
+    SrCur k; k.ps = nullptr; k.pq = nullptr; k.pm = nullptr;
+    p = mp_head_write(v, c, p);
+    *p++ = '\t'; p += put_u64(p, (uint64_t)s.cnt); *p++ = '\t';
+    if (s.nplp == 0) {
+        *p++ = '*'; *p++ = '\t'; *p++ = '*';
+        for (int i = 0; i < mp_n_opt_cols(cf); ++i) { *p++ = '\t'; *p++ = '*'; }
+    } else {
+        char *ps = p, *pq = ps + (s.seq_len ? s.seq_len : 1) + 1, *pm = pq + (s.cnt ? s.cnt : 1);
+        char *pend = cf.out_mapq ? pm + 1 + (s.cnt ? s.cnt : 1) : pm;
+        pq[-1] = '\t';
+        if (!s.cnt) { *ps = '*'; *pq = '*'; if (cf.out_mapq) { pm[0] = '\t'; pm[1] = '*'; } }
+        else { if (cf.out_mapq) *pm++ = '\t'; k.ps = ps; k.pq = pq; k.pm = pm; }
+        p = pend;
+        for (int i = 0; i < cf.n_star_cols; ++i) { *p++ = '\t'; *p++ = '*'; }
+    }
+    *p = '\n';
+    return k;
+}
+
+// generic entry of read i at column c: bytes appended at ps, or -1 when the base fails -Q
+PLP_HD int sr_slow_entry(const View &v, const MpConf &cf, int32_t i, int32_t c, char *ps, int &q)
+{
+    const ReadDesc d = load_desc(v.desc + i);
+    Ent e;
+    resolve(v, d, c, e);
+    q = ent_qual(v, d, e);
+    if (q < cf.min_baseQ) return -1;
+    return mp_entry_write(v, cf, d, v.cigar + d.cig_off, e, c, ps);
+}
+
+// append entry x of a staged read to the column's strings (mq = the read's mapq character)
+PLP_HD void sr_emit(uint32_t x, char mq, int out_mapq, SrCur &k)
+{
+    if (x & 0x80u) { *k.ps++ = '^'; *k.ps++ = mq; }
+    *k.ps++ = (char)(x & 0x7fu);
+    if (x & 0x8000u) *k.ps++ = '$';
+    *k.pq++ = (char)((x >> 8) & 0x7fu);
+    if (out_mapq) *k.pm++ = mq;
+}
+
+// reads that can cover the four 32-column groups g0..g0+3: far-reaching list of g0, then [lo(g0), hi(g0+3)).
+// (a read that is far-reaching for a later group and covers it also covers g0, so it is in one of the two parts)
+PLP_HD ReadRange sr_range(const View &v, int g0)
+{
+    ReadRange r;
+    int g3 = g0 + 3; if (g3 >= v.n_tiles) g3 = v.n_tiles - 1;
+    const int32_t o0 = v.ovf_off[g0];
+    r.n_ovf = v.ovf_off[g0 + 1] - o0;
+    r.ovf = v.ovf_idx + o0;
+    r.lo = v.tile_lo[g0];
+    int32_t hi = v.tile_hi[g3]; if (hi < r.lo) hi = r.lo;
+    r.n = r.n_ovf + (hi - r.lo);
+    return r;
+}
+
 // ---- depth (bam2depth.c) ------------------------------------------------------
 // In depth mode ReadDesc.rend is bam_endpos (zero-length reads span one column).
 struct DpCol { int32_t depth; bool spanned; };

@@ -202,7 +202,9 @@ PLP_HD void stage_build_desc(const RawSoA &r, const b200_stage_conf_t &cf, int64
         }
     }
     desc[i] = d;
-    endv[i] = d.rend > d.rpos ? d.rend : INT32_MIN;
+    // end used for the running max that bounds the per-group read slices: capped at rpos + kReach, because from
+    // there on the read is served through the far-reaching lists (k_ovf_*) and must not widen the slices under it
+    endv[i] = d.rend > d.rpos ? (d.rend - d.rpos > kReach ? d.rpos + kReach : d.rend) : INT32_MIN;
     if (keep) {
         PLP_ADD64(&acc->n_kept, 1);
         const int64_t wend = cf.end - win_base;   // may overflow int32 only on purpose-built inputs

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <queue>
 #include <string>
@@ -24,7 +25,7 @@ using namespace plp;
 struct b200_engine {
     std::string err, name;
     b200_batch_t b; b200_stage_conf_t cf;
-    std::vector<uint8_t> qual, mapq, state; std::vector<int32_t> rlen, endv, pmax, glo, ghi, clip, cig_x, cig_y, ovf_off, ovf_idx; std::vector<ReadDesc> desc;
+    std::vector<uint8_t> qual, seq4, mapq, state; std::vector<int32_t> rlen, endv, pmax, glo, ghi, clip, cig_x, cig_y, ovf_off, ovf_idx; std::vector<ReadDesc> desc;
     std::vector<int64_t> next, bedb, bede;
     std::string ref;
     StageAcc acc;
@@ -48,7 +49,7 @@ static RawSoA raw(b200_engine *e)
     RawSoA r;
     r.pos = b.pos; r.flag = b.flag; r.mapq = e->mapq.data(); r.l_qseq = b.l_qseq; r.n_cigar = b.n_cigar; r.cigar_off = b.cigar_off;
     r.qual_off = b.qual_off; r.mtid = b.mtid; r.mpos = b.mpos; r.isize = b.isize; r.prev = b.prev_same_name; r.rbits = b.rbits;
-    r.cigar = b.cigar; r.seq4 = b.seq4; r.qual = e->qual.data();
+    r.cigar = b.cigar; r.seq4 = e->seq4.data(); r.qual = e->qual.data();
     r.ref = b.ref && b.ref_len > 0 ? e->ref.data() : nullptr; r.ref_beg = b.ref_beg; r.ref_n = b.ref_n; r.ref_len = r.ref ? b.ref_len : 0;
     r.n = b.n_reads; r.tid = b.tid;
     return r;
@@ -92,6 +93,7 @@ static void build_ranges(b200_engine *e, int *max_range)
             if (g1 >= e->n_groups) g1 = e->n_groups - 1;
             for (int32_t g = g0; g <= g1; ++g) lists[(size_t)f * e->n_groups + g].push_back((int32_t)i);
         }
+    { size_t mo = 0; for (auto &l : lists) mo = std::max(mo, l.size()); *max_range += (int)mo; }
     e->ovf_off.assign(lists.size() + 2, 0); e->ovf_idx.clear();
     for (size_t k = 0; k < lists.size(); ++k) { e->ovf_off[k] = (int32_t)e->ovf_idx.size(); e->ovf_idx.insert(e->ovf_idx.end(), lists[k].begin(), lists[k].end()); }
     e->ovf_off[lists.size()] = (int32_t)e->ovf_idx.size(); e->ovf_off[lists.size() + 1] = (int32_t)e->ovf_idx.size();
@@ -102,7 +104,8 @@ int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t 
 {
     e->b = *b; e->cf = *cf; e->name = b->tid_name ? b->tid_name : "";
     const int64_t n = b->n_reads;
-    e->qual.assign(b->qual, b->qual + b->qual_bytes); e->qual.resize(b->qual_bytes + 8, 0);
+    e->qual.assign(b->qual, b->qual + b->qual_bytes); e->qual.resize(b->qual_bytes + 16, 0);
+    e->seq4.assign(b->seq4, b->seq4 + (b->qual_bytes + 1) / 2 + 1); e->seq4.resize(e->seq4.size() + 16, 0);
     e->mapq.assign(b->mapq, b->mapq + n); e->mapq.resize((size_t)n + 1);
     e->ref.assign(b->ref ? b->ref : "", b->ref ? (size_t)b->ref_n : 0);
     e->state.assign((size_t)n + 1, 0); e->rlen.assign((size_t)n + 1, 0); e->desc.assign((size_t)n + 1, ReadDesc());
@@ -182,7 +185,7 @@ int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t 
 static void fill_view(b200_engine *e, View &v, const int64_t *bb, const int64_t *be, int nb, int active, int all)
 {
     const b200_batch_t &b = e->b;
-    v.desc = e->desc.data(); v.cigar = b.cigar; v.cig_x = e->cig_x.data(); v.cig_y = e->cig_y.data(); v.seq4 = b.seq4; v.qual = e->qual.data();
+    v.desc = e->desc.data(); v.cigar = b.cigar; v.cig_x = e->cig_x.data(); v.cig_y = e->cig_y.data(); v.seq4 = e->seq4.data(); v.qual = e->qual.data();
     v.clip = e->has_clip ? e->clip.data() : nullptr;
     v.ref = (b.ref && b.ref_len > 0) ? e->ref.data() : nullptr;
     v.ref_off = b.ref_beg - e->win_base; v.ref_n = b.ref_n; v.ref_len_rel = (v.ref ? b.ref_len : 0) - e->win_base;
@@ -206,6 +209,76 @@ int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out,
     View v; fill_view(e, v, c->bed_beg, c->bed_end, c->n_bed, c->bed_active, c->all);
     MpConf cf{c->min_baseQ, c->all, c->rev_del, c->no_ins, c->no_del, c->no_ends, c->out_mapq, c->out_qpos, c->out_qpos5, c->n_star_cols};
     std::string s;
+    const char *sr = getenv("EMUL_SR");   // replay the opt-in staged-reads write kernel instead of the default one
+    if (v.n_files == 1 && !cf.out_qpos && !cf.out_qpos5 && sr && atoi(sr) == 1) {
+        // sequential replay of k_mp_sr_write (mpileup_sr.cuh): same building blocks, same slot/chunk structure
+        const int T = SR_COLS, S = 32;
+        const uint32_t ends = cf.no_ends ? 0u : 1u;
+        for (int32_t c0 = 0; c0 < v.ncols; c0 += T) {
+            std::vector<std::string> line(T);
+            std::vector<SrCur> cur(T);
+            uint32_t rb[T];
+            for (int t = 0; t < T; ++t) {
+                const int32_t c = c0 + t;
+                cur[t].ps = cur[t].pq = cur[t].pm = nullptr;
+                rb[t] = sr_ref_code(v, c);
+                if (c >= v.ncols) continue;
+                MpFileSz s0;
+                const uint32_t len = mp_line_size(v, cf, c >> 5, c, s0);
+                if (!len) continue;
+                line[t].assign(len, '?');
+                cur[t] = sr_layout(v, cf, c, s0, &line[t][0]);
+            }
+            const ReadRange rr = sr_range(v, c0 >> 5);
+            for (int32_t t0 = 0; t0 < rr.n; t0 += S) {
+                static uint32_t sq[S][SR_QROW], ss[S][SR_SROW];
+                uint32_t meta[S] = {0}; int32_t idx[S] = {0}; char mq[S] = {0};
+                memset(sq, 0xee, sizeof sq); memset(ss, 0xee, sizeof ss);   // stale contents must never matter
+                for (int sl = 0; sl < S; ++sl) {
+                    ReadDesc d; memset(&d, 0, sizeof d);
+                    if (t0 + sl < rr.n) {
+                        idx[sl] = range_at(rr, t0 + sl);
+                        d = load_hot(v.desc + idx[sl]);
+                        mq[sl] = (char)(d.mapq > 93 ? 126 : d.mapq + 33);
+                    }
+                    uint32_t qi;
+                    const uint32_t m = sr_meta(d, c0, ends, qi);
+                    meta[sl] = m;
+                    if (m & SR_SIMPLE) {
+                        const uint32_t nb = (m >> 8) & 0xffu;
+                        const uint32_t nwq = ((qi & 3u) + nb + 3u) >> 2, nws = ((qi & 7u) + nb + 7u) >> 3;
+                        for (uint32_t k = 0; k < nwq; ++k) memcpy(&sq[sl][k], v.qual + 4 * ((size_t)(qi >> 2) + k), 4);
+                        for (uint32_t k = 0; k < nws; ++k) memcpy(&ss[sl][k], v.seq4 + 4 * ((size_t)(qi >> 3) + k), 4);
+                    }
+                }
+                const int ns = std::min<int32_t>(S, rr.n - t0);
+                for (int t = 0; t < T; ++t) {
+                    if (!cur[t].ps) continue;
+                    for (int sl = 0; sl < ns; ++sl) {
+                        const uint32_t m = meta[sl];
+                        const uint32_t r = (uint32_t)t - (m & 0xffu);
+                        if (r >= ((m >> 8) & 0xffu)) continue;
+                        if (m & SR_SIMPLE) {
+                            const uint32_t nib = ((m >> 18) & 7u) + r;
+                            const uint8_t *q8 = (const uint8_t *)&sq[sl][0], *s8 = (const uint8_t *)&ss[sl][0];
+                            const uint32_t x = sr_entry(m, r, q8[((m >> 16) & 3u) + r], s8[nib >> 1], nib, rb[t], cf.min_baseQ, (const uint8_t *)".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn");
+                            if (!x) continue;
+                            sr_emit(x, mq[sl], cf.out_mapq, cur[t]);
+                        } else {
+                            int q;
+                            const int nb = sr_slow_entry(v, cf, idx[sl], c0 + t, cur[t].ps, q);
+                            if (nb < 0) continue;
+                            cur[t].ps += nb;
+                            *cur[t].pq++ = (char)(q + 33 < 126 ? q + 33 : 126);
+                            if (cf.out_mapq) *cur[t].pm++ = mq[sl];
+                        }
+                    }
+                }
+            }
+            for (int t = 0; t < T; ++t) s += line[t];
+        }
+        return emit(e, s, out, cap, out_len);
+    }
     for (int32_t col = 0; col < v.ncols; ++col) {
         MpFileSz s0;
         uint32_t len = mp_line_size(v, cf, col >> 5, col, s0);

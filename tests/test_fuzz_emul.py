@@ -42,3 +42,10 @@ def run_all(tool, oracle, td, seeds, need_noBAQ):
 def test_fuzz_host_and_column_code(emul_bin, oracle_bin, tmp_path):
     bad = run_all(emul_bin, oracle_bin, tmp_path, range(1, 41), need_noBAQ=True)
     assert not bad, f'{len(bad)} mismatches, first: {bad[0]}'
+
+
+def test_fuzz_staged_reads_blocks(emul_bin, oracle_bin, tmp_path, monkeypatch):
+    """Same cases through the building blocks of the opt-in staged-reads write kernel (mpileup_sr.cuh)."""
+    monkeypatch.setenv('EMUL_SR', '1')
+    bad = run_all(emul_bin, oracle_bin, tmp_path, range(1, 13), need_noBAQ=True)
+    assert not bad, f'{len(bad)} mismatches, first: {bad[0]}'

@@ -139,7 +139,7 @@ def test_c2_size_properties():
     soa = noref(synth.make_batch(length=1_000_000, depth=30, seed=2))
     digests = {}
     for tag, env in (('tma', {'B200_PLP_TMA': '1'}), ('vec', {'B200_PLP_TMA': '0'}), ('direct', {'B200_PLP_SMEM_TEXT': '1024'}),
-                     ('colmajor', {'B200_PLP_VARIANT': '1'}), ('rm_size', {'B200_PLP_STREAM_SIZE': '0'}), ('fourcol_write', {'B200_PLP_VARIANT': '4'}), ('fourcol_direct', {'B200_PLP_VARIANT': '4', 'B200_PLP_SMEM_TEXT': '1024'}), ('readmajor', {'B200_PLP_VARIANT': '2'}), ('readmajor_direct', {'B200_PLP_VARIANT': '2', 'B200_PLP_SMEM_TEXT': '1024'}), ('colmajor_direct', {'B200_PLP_VARIANT': '1', 'B200_PLP_SMEM_TEXT': '1024'}),
+                     ('staged_reads', {'B200_PLP_SR': '1'}), ('staged_reads_direct', {'B200_PLP_SR': '1', 'B200_PLP_SMEM_TEXT': '1024'}), ('colmajor', {'B200_PLP_VARIANT': '1'}), ('rm_size', {'B200_PLP_STREAM_SIZE': '0'}), ('fourcol_write', {'B200_PLP_VARIANT': '4'}), ('fourcol_direct', {'B200_PLP_VARIANT': '4', 'B200_PLP_SMEM_TEXT': '1024'}), ('readmajor', {'B200_PLP_VARIANT': '2'}), ('readmajor_direct', {'B200_PLP_VARIANT': '2', 'B200_PLP_SMEM_TEXT': '1024'}), ('colmajor_direct', {'B200_PLP_VARIANT': '1', 'B200_PLP_SMEM_TEXT': '1024'}),
                      ('chained', {'B200_PLP_CHAINED': '1'}), ('chained_direct', {'B200_PLP_CHAINED': '1', 'B200_PLP_SMEM_TEXT': '1024'})):
         os.environ.update(env)
         e = engine.Engine(0)
