@@ -190,6 +190,14 @@ int b200_pileup_entries(b200_engine_t *e, int32_t file, int64_t beg, int64_t end
                         b200_pileup1_t *entries, size_t cap_entries, size_t *n_entries);
 
 /* device timing of the last column-stage call (CUDA events on the engine stream), milliseconds */
+/* Benchmark support: repeat the device side of the read stage (everything b200_stage does after its host->device
+ * copies: filters, -6, BAQ, -C, descriptors, read slices, max-depth rule, overlap tweak) on the batch already resident in
+ * device memory.  The read stage edits qualities / mapq in place, so a pristine copy has to stay resident:
+ * call b200_set_keep_raw(e, 1) before b200_stage().  Replaces nothing in the reference; lets a device-resident
+ * measurement cover the whole hot path (bam_plcmd.c:400-461 + the column loop) without the PCIe copies. */
+int b200_set_keep_raw(b200_engine_t *e, int on);
+int b200_restage(b200_engine_t *e, b200_stage_stats_t *stats);
+double b200_last_stage_device_ms(const b200_engine_t *e);   /* device part of the last b200_stage / b200_restage */
 double b200_last_kernel_ms(const b200_engine_t *e);
 double b200_last_stage_ms(const b200_engine_t *e);
 int64_t b200_launch_count(const b200_engine_t *e);   /* kernels launched by this handle so far */

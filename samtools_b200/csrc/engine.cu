@@ -714,6 +714,8 @@ __global__ void k_apply_maxdrop(const uint8_t *state, ReadDesc *desc, int32_t *e
     if (state[i] == ST_MAXDROP) { desc[i].rend = desc[i].rpos; endv[i] = INT32_MIN; }
 }
 
+static int stage_device(b200_engine *e, b200_stage_stats_t *stats);
+
 extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t *cf, b200_stage_stats_t *stats)
 {
     if (!e || !b || !cf) return -1;
@@ -739,7 +741,11 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
     if (e->has_rbits) H2D(rbits, b->rbits, n);
     H2D(cigar, b->cigar, b->n_cigar_total);
     H2D(seq4, b->seq4, (b->qual_bytes + 1) / 2 + 1);
-    H2D(qual, b->qual, b->qual_bytes + 1);
+    e->qual_bytes = (size_t)b->qual_bytes + 1;
+    if (e->keep_raw) {       // a pristine copy stays resident so that b200_restage() can repeat the read stage (it edits qualities / mapq in place)
+        H2D(qual0, b->qual, b->qual_bytes + 1); H2D(mapq0, b->mapq, n);
+        ENSURE(qual, (size_t)b->qual_bytes + 1);
+    } else H2D(qual, b->qual, b->qual_bytes + 1);
     H2D(file_start, b->file_start, b->n_files + 1);
     e->has_ref = b->ref != nullptr && b->ref_len > 0;
     if (e->has_ref) H2D(ref, b->ref, b->ref_n);
@@ -748,9 +754,39 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
         size_t nl = strlen(e->name.c_str());
         H2D(dname, e->name.c_str(), nl + 1);
     }
+    e->n_cigar_total = (size_t)b->n_cigar_total;
+    e->has_host_clip = false;
+    if (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps && b->depth_clip && n > 0) {
+        // clip coordinates replayed by the caller (one name hash per file, across reference sequences)
+        e->h_clip_tmp.resize((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t cabs = b->depth_clip[i];
+            int64_t rel = cabs ? cabs - e->win_base : (int64_t)INT32_MIN;
+            if (rel > INT32_MAX) rel = INT32_MAX;
+            if (rel < INT32_MIN) rel = INT32_MIN;
+            e->h_clip_tmp[(size_t)i] = (int32_t)rel;
+        }
+        H2D(clip, e->h_clip_tmp.data(), n);
+        e->has_host_clip = true;
+    }
+    CK(cudaEventRecord(e->evA, e->stream));
+    e->uploaded = true;
+    return stage_device(e, stats);
+}
+
+// Device side of the read stage: per-read filters, -6, BAQ, -C, descriptors, per-group read slices, max-depth rule,
+// mate-overlap tweak.  Works on the arrays resident in device memory (b200_stage uploads them first).
+static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
+{
+    const int64_t n = e->n;
+    const b200_stage_conf_t *cf = &e->sconf;
+    if (e->keep_raw && n > 0) {
+        CK(cudaMemcpyAsync(e->qual, e->qual0, e->qual_bytes, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->mapq, e->mapq0, (size_t)n, cudaMemcpyDeviceToDevice, e->stream));
+    }
     ENSURE(state, (size_t)n + 1); ENSURE(rlen, (size_t)n + 1); ENSURE(desc, (size_t)n + 1);
     ENSURE(endv, (size_t)n + 1); ENSURE(pmax, (size_t)n + 1);
-    ENSURE(cig_x, (size_t)b->n_cigar_total + 1); ENSURE(cig_y, (size_t)b->n_cigar_total + 1);
+    ENSURE(cig_x, e->n_cigar_total + 1); ENSURE(cig_y, e->n_cigar_total + 1);
     CK(cudaMemsetAsync(e->d_acc, 0, sizeof(StageAcc), e->stream));
     {
         StageAcc z; memset(&z, 0, sizeof z); z.max_rend = INT32_MIN;
@@ -762,7 +798,7 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
     r.prev = e->has_prev ? e->prev : nullptr; r.rbits = e->has_rbits ? e->rbits : nullptr;
     r.cigar = e->cigar; r.seq4 = e->seq4; r.qual = e->qual;
     r.ref = e->has_ref ? e->ref : nullptr; r.ref_beg = e->ref_beg; r.ref_n = e->ref_n; r.ref_len = e->ref_len;
-    r.n = n; r.tid = b->tid;
+    r.n = n; r.tid = e->tid;
     StageAcc *acc = (StageAcc *)e->d_acc;
     if (n > 0) {
         k_prep1<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, acc); e->launches++;
@@ -782,7 +818,7 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
         int64_t wend = cf->end - e->win_base;                       // exclusive, relative
         int64_t cov = e->max_rend > 0 ? e->max_rend : 0;
         if (cov > wend) cov = wend;
-        int64_t allc = (cf->end < b->tid_len ? cf->end : b->tid_len) - e->win_base;
+        int64_t allc = (cf->end < e->tid_len ? cf->end : e->tid_len) - e->win_base;
         if (allc < 0) allc = 0;
         e->ncols_cov = cov; e->ncols_all = allc;
         int64_t nc = cov > allc ? cov : allc;
@@ -806,17 +842,7 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
             }
         }
         if (cf->mode == B200_MODE_MPILEUP && cf->overlaps && e->has_prev) { if (launch_overlap(e, r)) return -1; }
-        if (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps && b->depth_clip) {
-            // clip coordinates replayed by the caller (one name hash per file, across reference sequences)
-            e->h_clip_tmp.resize((size_t)n);
-            for (int64_t i = 0; i < n; ++i) {
-                const int64_t cabs = b->depth_clip[i];
-                int64_t rel = cabs ? cabs - e->win_base : (int64_t)INT32_MIN;
-                if (rel > INT32_MAX) rel = INT32_MAX;
-                if (rel < INT32_MIN) rel = INT32_MIN;
-                e->h_clip_tmp[(size_t)i] = (int32_t)rel;
-            }
-            H2D(clip, e->h_clip_tmp.data(), n);
+        if (e->has_host_clip) {
             e->has_clip = true;
         } else if (cf->mode == B200_MODE_DEPTH && cf->d_remove_overlaps && e->has_prev) { if (launch_depth_clip(e, r)) return -1; }
         else e->has_clip = false;
@@ -830,6 +856,7 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
     CK(cudaEventRecord(e->ev1, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_stage_ms = ms;
+    cudaEventElapsedTime(&ms, e->evA, e->ev1); e->last_stage_device_ms = ms;
     e->staged = true;
     if (stats) {
         stats->n_kept = (int64_t)ha.n_kept; stats->n_kept_in_window = (int64_t)ha.n_kept_in_window;
@@ -839,6 +866,25 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
     }
     return 0;
 }
+
+extern "C" int b200_set_keep_raw(b200_engine_t *e, int on)
+{
+    if (!e) return -1;
+    e->keep_raw = on != 0; e->uploaded = false; e->staged = false;
+    return 0;
+}
+
+extern "C" int b200_restage(b200_engine_t *e, b200_stage_stats_t *stats)
+{
+    if (!e) return -1;
+    if (!e->uploaded || !e->keep_raw) { snprintf(e->err, sizeof e->err, "b200_restage needs b200_set_keep_raw(e, 1) before b200_stage"); return -1; }
+    CK(cudaSetDevice(e->device));
+    e->staged = false;
+    CK(cudaEventRecord(e->ev0, e->stream));
+    CK(cudaEventRecord(e->evA, e->stream));
+    return stage_device(e, stats);
+}
+extern "C" double b200_last_stage_device_ms(const b200_engine_t *e) { return e ? e->last_stage_device_ms : 0; }
 
 int build_ranges(b200_engine *e, int *max_range)
 {

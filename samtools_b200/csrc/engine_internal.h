@@ -16,7 +16,9 @@ struct b200_engine {
     double last_parts_ms[3] = {0, 0, 0};
     char err[512];
     int64_t launches = 0;
-    double last_kernel_ms = 0, last_stage_ms = 0;
+    double last_kernel_ms = 0, last_stage_ms = 0, last_stage_device_ms = 0;
+    bool keep_raw = false, uploaded = false, has_host_clip = false;
+    size_t qual_bytes = 0, n_cigar_total = 0;
     uint32_t smem_text = 24 * 1024;
     int use_tma = 1, chained = 0, variant = 0, write_occ = 0, stream_size = 1, sr_write = 0;
     uint32_t smem_text_rm = 36 * 1024;
@@ -27,6 +29,7 @@ struct b200_engine {
     DBUF(int64_t, prev); DBUF(uint8_t, rbits);
     DBUF(uint32_t, cigar); DBUF(uint8_t, seq4); DBUF(uint8_t, qual); DBUF(char, ref); DBUF(char, dname);
     DBUF(int64_t, file_start);
+    DBUF(uint8_t, qual0); DBUF(uint8_t, mapq0);   // pristine copies for b200_restage (b200_set_keep_raw)
     // derived
     DBUF(uint8_t, state); DBUF(int32_t, rlen); DBUF(plp::ReadDesc, desc); DBUF(int32_t, endv); DBUF(int32_t, pmax);
     DBUF(int32_t, glo); DBUF(int32_t, ghi); DBUF(uint64_t, status); DBUF(char, out);
@@ -63,7 +66,7 @@ struct b200_engine {
     }
     void free_all()
     {
-        void *ps[] = { pos, flag, mapq, l_qseq, n_cigar, cigar_off, qual_off, mtid, mpos, isize, prev, rbits, cigar, seq4, qual,
+        void *ps[] = { qual0, mapq0, pos, flag, mapq, l_qseq, n_cigar, cigar_off, qual_off, mtid, mpos, isize, prev, rbits, cigar, seq4, qual,
                        ref, dname, file_start, state, rlen, desc, endv, pmax, glo, ghi, status, out, bed_beg, bed_end, col_n,
                        col_off, col_state, tile_total, ovf_cnt, ovf_off, ovf_idx, ss_diff, ss_nplp, ss_fail, ss_extra, status2, ents, clip, next, cig_x, cig_y, baq_f, baq_idx, gl_out, gl_n, gl_flag, d_beta, d_fk, d_lhet, d_q2p, d_qthr };
         for (void *p : ps) if (p) cudaFree(p);

@@ -25,21 +25,19 @@ __global__ void __launch_bounds__(256) k_ss_reads(View v, MpConf cf, int64_t n_r
         if (a >= b) continue;
         if (lane == 0) { atomicAdd(&diff[a], 1); atomicAdd(&diff[b], -1); }
         if (d.fl & RD_SIMPLE) {
-            const uint32_t qbase = d.qoff + (uint32_t)d.qstart - (uint32_t)d.rpos;
-            for (int32_t c0 = a + lane; c0 < b; c0 += 32 * 8) {       // eight independent loads in flight per lane
-                int q[8];
+            const uint32_t qbase = d.qoff + (uint32_t)d.qstart - (uint32_t)d.rpos;   // query index = column + (qstart - rpos)
+            // "^"+mapq (2 bytes) at the read's first column and "$" (1) at its last, when that base passes -Q: two lanes
+            if (ends && lane < 2) {
+                const int32_t c = lane ? d.rend - 1 : d.rpos;
+                if (c >= a && c < b && (int)v.qual[qbase + (uint32_t)c] >= cf.min_baseQ) atomicAdd(&extra[c], lane ? 1u : 2u);
+            }
+            // every other base only matters when it FAILS -Q (sparse); five independent loads in flight per lane
+            for (int32_t c0 = a + lane; c0 < b; c0 += 32 * 5) {
+                int q[5];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) { const int32_t c = c0 + 32 * k; q[k] = c < b ? (int)v.qual[qbase + (uint32_t)c] : 255; }
+                for (int k = 0; k < 5; ++k) { const int32_t c = c0 + 32 * k; q[k] = c < b ? (int)v.qual[qbase + (uint32_t)c] : 255; }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int32_t c = c0 + 32 * k;
-                    if (c >= b) break;
-                    if (q[k] < cf.min_baseQ) atomicAdd(&fail[c], 1u);
-                    else {
-                        const uint32_t x = (ends & (uint32_t)(c == d.rpos)) * 2u + (ends & (uint32_t)(c == d.rend - 1));
-                        if (x) atomicAdd(&extra[c], x);
-                    }
-                }
+                for (int k = 0; k < 5; ++k) if (q[k] < cf.min_baseQ && c0 + 32 * k < b) atomicAdd(&fail[c0 + 32 * k], 1u);
             }
         } else {
             load_cold(d, v.desc + i);

@@ -18,7 +18,7 @@ POS_MAX = (0x7fffffff << 32) | 0xffffffff
 
 EXPORTS = ['b200_engine_create', 'b200_engine_destroy', 'b200_last_error', 'b200_version', 'b200_stage',
            'b200_mpileup_text', 'b200_depth_text', 'b200_coverage', 'b200_glf', 'b200_fetch_qual',
-           'b200_fetch_mapq_keep', 'b200_pileup_entries', 'b200_last_kernel_ms', 'b200_last_stage_ms',
+           'b200_fetch_mapq_keep', 'b200_pileup_entries', 'b200_last_kernel_ms', 'b200_last_stage_ms', 'b200_set_keep_raw', 'b200_restage', 'b200_last_stage_device_ms',
            'b200_launch_count', 'b200_last_mpileup_parts_ms']
 
 
@@ -92,6 +92,9 @@ def load_library():
         lib.b200_pileup_entries.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         lib.b200_last_kernel_ms.argtypes = [C.c_void_p]; lib.b200_last_kernel_ms.restype = C.c_double
         lib.b200_last_stage_ms.argtypes = [C.c_void_p]; lib.b200_last_stage_ms.restype = C.c_double
+        lib.b200_last_stage_device_ms.argtypes = [C.c_void_p]; lib.b200_last_stage_device_ms.restype = C.c_double
+        lib.b200_set_keep_raw.argtypes = [C.c_void_p, C.c_int]; lib.b200_set_keep_raw.restype = C.c_int
+        lib.b200_restage.argtypes = [C.c_void_p, C.c_void_p]; lib.b200_restage.restype = C.c_int
         lib.b200_launch_count.argtypes = [C.c_void_p]; lib.b200_launch_count.restype = C.c_int64
         lib.b200_last_mpileup_parts_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double * 3)]
         _lib = lib
@@ -167,6 +170,17 @@ class Engine:
             self._err('b200_stage')
         return st
 
+    def set_keep_raw(self, on=True):
+        """keep pristine qualities / mapq resident so that restage() can repeat the device side of the read stage"""
+        if self.lib.b200_set_keep_raw(self.h, 1 if on else 0) != 0:
+            self._err('b200_set_keep_raw')
+
+    def restage(self):
+        st = StageStats()
+        if self.lib.b200_restage(self.h, C.byref(st)) != 0:
+            self._err('b200_restage')
+        return st
+
     def _text(self, fn, conf, out=None, fetch=True):
         n = C.c_size_t(0)
         if not fetch:
@@ -229,6 +243,10 @@ class Engine:
     @property
     def last_stage_ms(self):
         return self.lib.b200_last_stage_ms(self.h)
+
+    @property
+    def last_stage_device_ms(self):
+        return self.lib.b200_last_stage_device_ms(self.h)
 
     @property
     def last_mpileup_parts_ms(self):

@@ -133,6 +133,21 @@ def test_pileup_entries_tier(synth_set, eng):
     assert (ents['qpos'] >= 0).all() and (ents['read'] < len(soa['pos'])).all()
 
 
+def test_restage_repeats_read_stage(synth_set):
+    """b200_restage (device-resident repeat of the read stage, used by bench.py) gives the same bytes as a fresh b200_stage,
+    also when the stage edits qualities in place (BAQ, overlap tweak, -C)."""
+    from samtools_b200 import engine
+    soa = synth_set['soa']
+    conf = engine.default_stage_conf(engine.MODE_MPILEUP, capq_thres=50)
+    e1 = engine.Engine(0); e1.stage(soa, conf); want = e1.mpileup_text(all=1); e1.close()
+    e2 = engine.Engine(0); e2.set_keep_raw(True); e2.stage(soa, conf)
+    got0 = e2.mpileup_text(all=1)
+    e2.restage(); got1 = e2.mpileup_text(all=1)
+    e2.restage(); got2 = e2.mpileup_text(all=1)
+    e2.close()
+    assert got0 == want and got1 == want and got2 == want
+
+
 # ---------------------------------------------------------------- full-size properties (BASELINE C2)
 def test_c2_size_properties():
     from samtools_b200 import engine, synth
