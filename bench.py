@@ -174,7 +174,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--region-mb', type=float, default=8.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-handles', type=int, default=2,
+    ap.add_argument('--e2e-handles', type=int, default=3,
                     help='engine handles (one host thread each) used by the end-to-end loop; handles are per-thread objects like the htslib iterators they replace')
     args = ap.parse_args()
     if args.impl == 'reference':
