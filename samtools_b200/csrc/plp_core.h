@@ -493,40 +493,56 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
         }
         const bool ends = !cf.no_ends, extras = (cf.out_mapq | cf.out_qpos | cf.out_qpos5) != 0;
         const int minq = cf.min_baseQ;
+        // Descriptors travel through the loop as four raw words (rpos, rend, qoff, qstart | mapq << 16 | flags << 24):
+        // rotating a struct with sub-word fields through the software pipeline costs ~25 byte-permute / move instructions
+        // per iteration.  Reads that are not of the simple shape reload their full descriptor in the (rare) generic branch.
+        struct Raw { int32_t rpos, rend; uint32_t qoff, pk; };
+        auto load_raw = [&](int32_t i) -> Raw {
+            Raw r;
+#if defined(__CUDA_ARCH__)
+            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(v.desc + i));
+            r.rpos = (int32_t)w.x; r.rend = (int32_t)w.y; r.qoff = w.z; r.pk = w.w;
+#else
+            const ReadDesc &d = v.desc[i];
+            r.rpos = d.rpos; r.rend = d.rend; r.qoff = d.qoff; r.pk = (uint32_t)d.qstart | (uint32_t)d.mapq << 16 | (uint32_t)d.fl << 24;
+#endif
+            return r;
+        };
+        const uint32_t kSimple = (uint32_t)RD_SIMPLE << 24, kRev = (uint32_t)RD_REV << 24;
         // operands of a simple read's entry, fetched one iteration ahead of their use
         struct Pre { int q; uint32_t sb; };
-        auto prefetch = [&](const ReadDesc &d) -> Pre {
+        auto prefetch = [&](const Raw &d) -> Pre {
             Pre o; o.q = 0; o.sb = 0;
             const uint32_t rel = (uint32_t)(c - d.rpos);
-            if (rel < (uint32_t)(d.rend - d.rpos) && (d.fl & RD_SIMPLE)) {
-                const uint32_t qi = d.qoff + (uint32_t)d.qstart + rel;
+            if (rel < (uint32_t)(d.rend - d.rpos) && (d.pk & kSimple)) {
+                const uint32_t qi = d.qoff + (d.pk & 0xffffu) + rel;
                 o.q = (int)v.qual[qi];
                 o.sb = v.seq4[qi >> 1];
             }
             return o;
         };
-        auto body = [&](ReadDesc d, int32_t i, const Pre &pre) {
-            const uint32_t rel = (uint32_t)(c - d.rpos);
-            if (rel >= (uint32_t)(d.rend - d.rpos)) return;
+        auto body = [&](const Raw &r, int32_t i, const Pre &pre) {
+            const uint32_t rel = (uint32_t)(c - r.rpos);
+            if (rel >= (uint32_t)(r.rend - r.rpos)) return;
             int q, qpos1 = 0; int32_t q5 = 0;
-            if (d.fl & RD_SIMPLE) {
-                const uint32_t qi = d.qoff + (uint32_t)d.qstart + rel;
+            const int mapq = (int)((r.pk >> 16) & 0xffu);
+            if (r.pk & kSimple) {
                 q = pre.q;
-                const uint32_t sb = pre.sb;
                 if (q < minq) return;
-                const bool rev = d.fl & RD_REV;
-                if (ends && rel == 0) { *ps++ = '^'; *ps++ = (char)(d.mapq > 93 ? 126 : d.mapq + 33); }
-                int ch = (sb >> ((~qi & 1) << 2)) & 0xf;
+                const bool rev = (r.pk & kRev) != 0;
+                const uint32_t par = (r.qoff ^ r.pk ^ rel) & 1u;          // parity of the query index qoff + qstart + rel
+                if (ends && rel == 0) { *ps++ = '^'; *ps++ = (char)(mapq > 93 ? 126 : mapq + 33); }
+                int ch = (int)((pre.sb >> ((par ^ 1u) << 2)) & 0xfu);
                 if (ch == rb) ch = 0;
                 *ps++ = base_char(ch, rev);
-                if (ends && c == d.rend - 1) *ps++ = '$';
+                if (ends && c == r.rend - 1) *ps++ = '$';
                 if (extras) {
-                    const int32_t qpos = (int32_t)d.qstart + (int32_t)rel;
+                    const int32_t qpos = (int32_t)(r.pk & 0xffffu) + (int32_t)rel;
                     qpos1 = qpos + 1;
-                    if (cf.out_qpos5) { load_cold(d, v.desc + i); q5 = rev ? d.l_qseq - qpos : qpos + 1; }
+                    if (cf.out_qpos5) { ReadDesc d; load_cold(d, v.desc + i); q5 = rev ? d.l_qseq - qpos : qpos + 1; }
                 }
             } else {
-                load_cold(d, v.desc + i);
+                const ReadDesc d = load_desc(v.desc + i);
                 const uint32_t *cg = v.cigar + d.cig_off;
                 Ent e;
                 resolve(v, d, c, e);
@@ -537,25 +553,25 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
             }
             *pq++ = (char)(q + 33 < 126 ? q + 33 : 126);
             if (extras) {
-                if (cf.out_mapq) { int m = d.mapq + 33; *pm++ = (char)(m > 126 ? 126 : m); }
+                if (cf.out_mapq) { int m = mapq + 33; *pm++ = (char)(m > 126 ? 126 : m); }
                 if (cf.out_qpos) { if (n) *pb++ = ','; pb += put_i32(pb, qpos1); }
                 if (cf.out_qpos5) { if (n) *pb5++ = ','; pb5 += put_i32(pb5, q5); }
                 ++n;
             }
         };
-        for (int32_t t_ = 0; t_ < rr.n_ovf; ++t_) { const int32_t i = rr.ovf[t_]; const ReadDesc d = load_hot(v.desc + i); body(d, i, prefetch(d)); }
+        for (int32_t t_ = 0; t_ < rr.n_ovf; ++t_) { const int32_t i = rr.ovf[t_]; const Raw d = load_raw(i); body(d, i, prefetch(d)); }
         const int32_t hi_ = rr.lo + (rr.n - rr.n_ovf);
         if (rr.lo < hi_) {
             // two-deep software pipeline: while entry i is formatted, the quality/base bytes of read i+1 and the
             // descriptor of read i+2 are in flight (the loop is bound by dependent-load latency otherwise)
-            ReadDesc d0 = load_hot(v.desc + rr.lo);
-            ReadDesc d1 = rr.lo + 1 < hi_ ? load_hot(v.desc + rr.lo + 1) : d0;
+            Raw d0 = load_raw(rr.lo);
+            Raw d1 = rr.lo + 1 < hi_ ? load_raw(rr.lo + 1) : d0;
             Pre p0 = prefetch(d0);
             for (int32_t i = rr.lo; i < hi_; ++i) {
-                const ReadDesc d = d0; const Pre pr = p0;
+                const Raw d = d0; const Pre pr = p0;
                 d0 = d1;
                 if (i + 1 < hi_) p0 = prefetch(d0);
-                if (i + 2 < hi_) d1 = load_hot(v.desc + i + 2);
+                if (i + 2 < hi_) d1 = load_raw(i + 2);
                 body(d, i, pr);
             }
         }
