@@ -40,3 +40,33 @@ def max_over_ranks(x, device='cpu'):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def gather_payload(local, sizes, dst=0):
+    """Variable-size gather of the shards' output bytes to rank `dst`, in shard (= genome) order
+    (all_gather of byte counts -> exclusive scan -> point-to-point payload).
+
+    local: 1-D uint8 tensor holding this rank's bytes (CUDA tensor over NCCL, CPU tensor over gloo);
+    sizes: per-rank byte counts, column 0 of gather_summaries().  Returns the concatenation on `dst`,
+    None elsewhere.  Not on bench.py's timed path: a production run lets every rank emit its own
+    region (the summaries give the order and the offsets), because funnelling all text through one
+    rank's PCIe link would serialise the job; this is for callers that need a single stream."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sizes = [int(x) for x in sizes]
+    if rank != dst:
+        if sizes[rank]:
+            dist.send(local[:sizes[rank]].contiguous(), dst=dst)
+        return None
+    out = torch.empty(sum(sizes), dtype=torch.uint8, device=local.device)
+    off = 0
+    for r in range(world):
+        n = sizes[r]
+        if n:
+            if r == dst:
+                out[off:off + n] = local[:n]
+            else:
+                dist.recv(out[off:off + n], src=r)
+        off += n
+    return out

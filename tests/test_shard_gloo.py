@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the only multi-GPU exchange on the path: region
-shard planning + the all_gather of per-shard column summaries (CPU tensors)."""
+shard planning, the all_gather of per-shard column summaries and the variable-size payload gather (CPU tensors)."""
 import os, socket, sys
 import torch
 import torch.multiprocessing as mp
@@ -21,7 +21,11 @@ def _worker(rank, world, port, q):
     # each rank "emits" a number of bytes that depends on its region
     allv, off = shard.gather_summaries([1000 + 7 * rank + (end - beg), end - beg, 3 * rank])
     mx = shard.max_over_ranks(1.5 + rank)
-    q.put((rank, plan, allv.tolist(), off, mx))
+    # variable-size payload gather to rank 0 in shard order (rank r emits 5 + 3 r bytes, all equal to 65 + r)
+    n = 5 + 3 * rank
+    sizes, _ = shard.gather_summaries([n])
+    cat = shard.gather_payload(torch.full((n + 2,), 65 + rank, dtype=torch.uint8), sizes[:, 0].tolist())
+    q.put((rank, plan, allv.tolist(), off, mx, None if cat is None else bytes(cat.tolist())))
     dist.destroy_process_group()
 
 
@@ -36,10 +40,11 @@ def test_region_shards_and_summary_gather():
     plan = res[0][1]
     assert plan[0][0] == 0 and plan[-1][1] == 10_000_001 and plan[0][1] == plan[1][0]     # contiguous, covering
     assert all((e - b) % 4096 == 0 for b, e in plan[:-1])
-    for rank, _, allv, off, mx in res:
+    for rank, _, allv, off, mx, cat in res:
         assert allv == res[0][2]                      # every rank sees the same table
         assert off == sum(r[0] for r in allv[:rank])   # exclusive prefix of bytes = this shard's output offset
         assert mx == 2.5
+        assert cat == (b'A' * 5 + b'B' * 8 if rank == 0 else None)   # payload concatenated in shard order on rank 0 only
 
 
 def test_single_process_paths():
@@ -49,3 +54,5 @@ def test_single_process_paths():
     assert allv.tolist() == [[5, 6, 7]] and off == 0
     assert shard.max_over_ranks(3.25) == 3.25
     assert shard.plan_shards(100, 1) == [(0, 100)]
+    t = torch.arange(4, dtype=torch.uint8)
+    assert shard.gather_payload(t, [4]) is t
