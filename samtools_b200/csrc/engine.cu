@@ -432,6 +432,21 @@ __global__ void __launch_bounds__(TILE) k_mpileup_write(MpFmt fmt, const uint32_
 {
     text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
 }
+// opt-in (B200_PLP_LEAN=1): the lean per-read loop of plp_core.h::mp_line_write_lean (single file, no -s / -O columns).
+// Bit-exact against the goldens and the fuzz cases on the emulation harness; NOT yet run or timed on a GPU.
+struct MpLeanFmt {
+    View v; MpConf cf; const uint8_t *tab;
+    typedef MpFileSz State;
+    __device__ __forceinline__ void write(int32_t c, const State &s, char *p) const { mp_line_write_lean(v, cf, c, s, p, tab); }
+};
+__global__ void __launch_bounds__(TILE) k_mpileup_write_lean(MpLeanFmt fmt, const uint32_t *len, const MpFileSz *st, const uint64_t *tile_base,
+                                                             char *out, uint32_t smem_cap, int use_tma)
+{
+    __shared__ uint8_t s_tab[32];
+    if (threadIdx.x < 32) s_tab[threadIdx.x] = (uint8_t)".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn"[threadIdx.x];   // visible after the barriers of the tile scan
+    fmt.tab = s_tab;
+    text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
+}
 // same kernel compiled for 12 resident CTAs per SM (<= 40 registers): the loop is latency-bound, occupancy pays
 __global__ void __launch_bounds__(TILE, 12) k_mpileup_write_occ(MpFmt fmt, const uint32_t *len, const MpFileSz *st, const uint64_t *tile_base,
                                                                char *out, uint32_t smem_cap, int use_tma)
@@ -639,6 +654,8 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     s = getenv("B200_PLP_WRITE_OCC"); e->write_occ = s ? atoi(s) : 0;
     s = getenv("B200_PLP_STREAM_SIZE"); e->stream_size = s ? atoi(s) : 1;
     s = getenv("B200_PLP_SR"); e->sr_write = s ? atoi(s) : 0;
+    s = getenv("B200_PLP_LEAN"); e->lean_write = s ? atoi(s) : 0;
+    cudaFuncSetAttribute(k_mpileup_write_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_mp_sr_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     cudaFuncSetAttribute(k_mpileup_write_occ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
     s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + one-column-per-thread write (default), 1: column-major both, 2: read-major both, 4: read-major sizing + 4-columns-per-thread write
@@ -1066,7 +1083,10 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
         const int ntw = (ncols + TILE - 1) / TILE;
         if (e->sr_write && e->variant == 0 && e->n_files == 1 && !c->out_qpos && !c->out_qpos5)
             k_mp_sr_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
-        else if (e->write_occ) k_mpileup_write_occ<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        else if (e->lean_write && e->variant == 0 && e->n_files == 1 && !c->out_mapq && !c->out_qpos && !c->out_qpos5) {
+            MpLeanFmt lf; lf.v = fmt.v; lf.cf = fmt.cf; lf.tab = nullptr;
+            k_mpileup_write_lean<<<ntw, TILE, e->smem_text + 16, e->stream>>>(lf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        } else if (e->write_occ) k_mpileup_write_occ<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
         else k_mpileup_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
     }
     e->launches++;

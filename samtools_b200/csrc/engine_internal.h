@@ -20,7 +20,7 @@ struct b200_engine {
     bool keep_raw = false, uploaded = false, has_host_clip = false;
     size_t qual_bytes = 0, n_cigar_total = 0;
     uint32_t smem_text = 24 * 1024;
-    int use_tma = 1, chained = 0, variant = 0, write_occ = 0, stream_size = 1, sr_write = 0;
+    int use_tma = 1, chained = 0, variant = 0, write_occ = 0, stream_size = 1, sr_write = 0, lean_write = 0;
     uint32_t smem_text_rm = 36 * 1024;
 
     // raw SoA image of the staged records

@@ -749,6 +749,98 @@ PLP_HD ReadRange sr_range(const View &v, int g0)
     return r;
 }
 
+// ---- lean write loop (opt-in B200_PLP_LEAN=1; single file, no -s / -O columns) -----------------
+// Same output as mp_line_write.  Differences, all aimed at the instruction count of the per-read iteration:
+//   * descriptors are four raw words; the three in flight rotate by NAME (loop unrolled by the pipeline depth)
+//     instead of by register moves;
+//   * the far-reaching list and the contiguous slice are one index space (no second copy of the loop);
+//   * the base character comes from a 32-byte table (shared memory on the device) instead of packed immediates;
+//   * reads that are not of the simple shape leave the fast loop through ONE cold block (goto), after which
+//     the pipeline is primed again -- a few hundred cycles once or twice per column instead of a copy of the
+//     generic formatter in every unrolled step.
+PLP_HD void mp_line_write_lean(const View &v, const MpConf &cf, int32_t c, const MpFileSz &s, char *p, const uint8_t *tab /* ".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn" */)
+{
+    const SrCur cur = sr_layout(v, cf, c, s, p);       // header, count, separators, place holders, newline
+    if (!cur.ps) return;
+    char *ps = cur.ps, *pq = cur.pq;
+    const ReadRange rr = read_range(v, 0, c >> 5);
+    const int32_t n = rr.n;
+    const int rb = (int)sr_ref_code(v, c);             // 0x10 without a FASTA: equal to no base code
+    const bool ends = !cf.no_ends;
+    const int minq = cf.min_baseQ;
+    struct Raw { int32_t rpos, rend; uint32_t qoff, pk; };
+    struct Pre { int q; uint32_t sb; };
+    static_assert(RD_REV == 1, "the table index below takes RD_REV from bit 24 of the packed word");
+    const uint32_t kSimple = (uint32_t)RD_SIMPLE << 24;
+    auto ridx = [&](int32_t t) -> int32_t { return t < rr.n_ovf ? rr.ovf[t] : rr.lo + (t - rr.n_ovf); };
+    auto load_raw = [&](int32_t t) -> Raw {
+        Raw r;
+        const int32_t i = ridx(t);
+#if defined(__CUDA_ARCH__)
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(v.desc + i));
+        r.rpos = (int32_t)w.x; r.rend = (int32_t)w.y; r.qoff = w.z; r.pk = w.w;
+#else
+        const ReadDesc &d = v.desc[i];
+        r.rpos = d.rpos; r.rend = d.rend; r.qoff = d.qoff; r.pk = (uint32_t)d.qstart | (uint32_t)d.mapq << 16 | (uint32_t)d.fl << 24;
+#endif
+        return r;
+    };
+    auto prefetch = [&](const Raw &d) -> Pre {
+        Pre o; o.q = 0; o.sb = 0;
+        const uint32_t rel = (uint32_t)(c - d.rpos);
+        if (rel < (uint32_t)(d.rend - d.rpos) && (d.pk & kSimple)) {
+            const uint32_t qi = d.qoff + (d.pk & 0xffffu) + rel;
+            o.q = (int)v.qual[qi];
+            o.sb = v.seq4[qi >> 1];
+        }
+        return o;
+    };
+    // formats the entry of a simple read; returns true when the read covers the column but needs the generic formatter
+    auto fast = [&](const Raw &r, const Pre &pre) -> bool {
+        const uint32_t rel = (uint32_t)(c - r.rpos);
+        if (rel >= (uint32_t)(r.rend - r.rpos)) return false;
+        if (!(r.pk & kSimple)) return true;
+        if (pre.q < minq) return false;
+        const uint32_t par = (r.qoff ^ r.pk ^ rel) & 1u;                  // parity of the query index qoff + qstart + rel
+        if (ends && rel == 0) { const int mapq = (int)((r.pk >> 16) & 0xffu); *ps++ = '^'; *ps++ = (char)(mapq > 93 ? 126 : mapq + 33); }
+        int ch = (int)((pre.sb >> ((par ^ 1u) << 2)) & 0xfu);
+        if (ch == rb) ch = 0;
+        *ps++ = (char)tab[((r.pk >> 20) & 0x10u) | (uint32_t)ch];          // RD_REV is bit 24 of pk -> +16: the reverse-strand half
+        if (ends && c == r.rend - 1) *ps++ = '$';
+        *pq++ = (char)(pre.q + 33 < 126 ? pre.q + 33 : 126);
+        return false;
+    };
+    int32_t t = 0;
+    while (t < n) {
+        const int32_t last = n - 1;
+        Raw dA = load_raw(t), dB = load_raw(t + 1 < n ? t + 1 : last), dC;
+        Pre pc = prefetch(dA), pn;
+        // one step: bytes of read t+1 and descriptor of read t+2 go in flight, entry t is formatted
+#define PLP_LEAN_STEP(CUR, NXT, NEW)                             \
+        pn = t + 1 < n ? prefetch(NXT) : pc;                     \
+        NEW = load_raw(t + 2 < n ? t + 2 : last);                \
+        if (fast(CUR, pc)) goto generic_entry;                   \
+        pc = pn; ++t;
+        while (t + 2 < n) { PLP_LEAN_STEP(dA, dB, dC) PLP_LEAN_STEP(dB, dC, dA) PLP_LEAN_STEP(dC, dA, dB) }
+        if (t < n) { PLP_LEAN_STEP(dA, dB, dC) }
+        if (t < n) { PLP_LEAN_STEP(dB, dC, dA) }
+#undef PLP_LEAN_STEP
+        break;
+    generic_entry:
+        {   // read t is not of the simple shape (indel / ref-skip / pad): the one copy of the generic formatter
+            const ReadDesc d = load_desc(v.desc + ridx(t));
+            Ent e;
+            resolve(v, d, c, e);
+            const int q = ent_qual(v, d, e);
+            if (q >= minq) {
+                ps += mp_entry_write(v, cf, d, v.cigar + d.cig_off, e, c, ps);
+                *pq++ = (char)(q + 33 < 126 ? q + 33 : 126);
+            }
+            ++t;
+        }
+    }
+}
+
 // ---- depth (bam2depth.c) ------------------------------------------------------
 // In depth mode ReadDesc.rend is bam_endpos (zero-length reads span one column).
 struct DpCol { int32_t depth; bool spanned; };

@@ -279,12 +279,15 @@ int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out,
         }
         return emit(e, s, out, cap, out_len);
     }
+    const char *lean = getenv("EMUL_LEAN");   // replay the opt-in lean write loop (mp_line_write_lean) where it applies
+    const bool use_lean = lean && atoi(lean) == 1 && v.n_files == 1 && !cf.out_mapq && !cf.out_qpos && !cf.out_qpos5;
     for (int32_t col = 0; col < v.ncols; ++col) {
         MpFileSz s0;
         uint32_t len = mp_line_size(v, cf, col >> 5, col, s0);
         if (!len) continue;
         size_t at = s.size(); s.resize(at + len, '?');
-        mp_line_write(v, cf, col >> 5, col, s0, &s[at]);
+        if (use_lean) mp_line_write_lean(v, cf, col, s0, &s[at], (const uint8_t *)".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn");
+        else mp_line_write(v, cf, col >> 5, col, s0, &s[at]);
     }
     return emit(e, s, out, cap, out_len);
 }

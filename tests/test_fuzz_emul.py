@@ -49,3 +49,10 @@ def test_fuzz_staged_reads_blocks(emul_bin, oracle_bin, tmp_path, monkeypatch):
     monkeypatch.setenv('EMUL_SR', '1')
     bad = run_all(emul_bin, oracle_bin, tmp_path, range(1, 13), need_noBAQ=True)
     assert not bad, f'{len(bad)} mismatches, first: {bad[0]}'
+
+
+def test_fuzz_lean_write_loop(emul_bin, oracle_bin, tmp_path, monkeypatch):
+    """Same cases through the opt-in lean write loop (plp_core.h::mp_line_write_lean, B200_PLP_LEAN=1 on the device)."""
+    monkeypatch.setenv('EMUL_LEAN', '1')
+    bad = run_all(emul_bin, oracle_bin, tmp_path, range(1, 13), need_noBAQ=True)
+    assert not bad, f'{len(bad)} mismatches, first: {bad[0]}'
