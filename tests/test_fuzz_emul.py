@@ -13,7 +13,10 @@ def emul_bin():
 
 
 def run_all(tool, oracle, td, seeds, need_noBAQ):
-    bad = []
+    """every (seed, command line): oracle output vs tool output; a few processes in flight (the cases are independent
+    and read-only; on the GPU each tool process pays ~1 s of CUDA context creation)"""
+    from concurrent.futures import ThreadPoolExecutor
+    tasks = []
     for seed in seeds:
         sam, fa = fuzz_sam.make_sam(seed)
         d = td / f's{seed}'; d.mkdir()
@@ -31,12 +34,17 @@ def run_all(tool, oracle, td, seeds, need_noBAQ):
             opt = opt.format(bed='x.bed', rg='rg.txt')
             files = 'x.sam x2.sam' if (seed % 3 == 0 and '-r' not in opt) else 'x.sam'
             ref = '-f x.fa' if cmd == 'mpileup' and seed % 4 != 1 else ''
-            line = f'{cmd} {opt} {ref} {files}'
-            a = subprocess.run(f'{oracle} {line}', shell=True, cwd=d, capture_output=True)
-            b = subprocess.run(f'{tool} {line}', shell=True, cwd=d, capture_output=True)
-            if a.stdout != b.stdout or (a.returncode == 0) != (b.returncode == 0):
-                bad.append((seed, line, a.stdout[:200], b.stdout[:200], b.stderr[-200:]))
-    return bad
+            tasks.append((seed, f'{cmd} {opt} {ref} {files}', d))
+
+    def one(t):
+        seed, line, d = t
+        a = subprocess.run(f'{oracle} {line}', shell=True, cwd=d, capture_output=True)
+        b = subprocess.run(f'{tool} {line}', shell=True, cwd=d, capture_output=True)
+        if a.stdout != b.stdout or (a.returncode == 0) != (b.returncode == 0):
+            return (seed, line, a.stdout[:200], b.stdout[:200], b.stderr[-200:])
+        return None
+    with ThreadPoolExecutor(max_workers=int(os.environ.get('B200_TEST_JOBS', '6'))) as ex:
+        return [r for r in ex.map(one, tasks) if r is not None]
 
 
 def test_fuzz_host_and_column_code(emul_bin, oracle_bin, tmp_path):

@@ -9,7 +9,7 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 CASES = golden_cases.all_cases()
-CLI = os.path.join(ROOT, 'samtools_b200', 'bin', 'b200samtools')
+CLI = os.environ.get('B200_TEST_CLI') or os.path.join(ROOT, 'samtools_b200', 'bin', 'b200samtools')
 
 
 @pytest.fixture(scope='module')
@@ -18,11 +18,38 @@ def cli():
     return CLI
 
 
+@pytest.fixture(scope='module')
+def golden_results(cli, oracle_bin, corpus):
+    """All golden command lines, run once up front with a few processes in flight (each CLI process pays ~1 s of CUDA
+    context creation; serially the 160+ cases take four minutes).  Lines that write a scratch file into the corpus
+    directory (`sed ... > sample1.sam; ...`) run one at a time afterwards.  Results are checked per case below."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def run(c):
+        try:
+            return golden_cases.run_case(c, cli, oracle_bin, corpus)
+        except Exception as e:          # timeout etc.: reported by the case's own test
+            return e
+    todo = [c for c in CASES if not c['skip']]
+    par = [c for c in todo if '>' not in c['cmd']]
+    ser = [c for c in todo if '>' in c['cmd']]
+    res = {}
+    with ThreadPoolExecutor(max_workers=int(os.environ.get('B200_TEST_JOBS', '6'))) as ex:
+        for c, r in zip(par, ex.map(run, par)):
+            res[c['id']] = r
+    for c in ser:
+        res[c['id']] = run(c)
+    return res
+
+
 @pytest.mark.parametrize('case', CASES, ids=[c['id'] for c in CASES])
-def test_reference_golden_on_gpu(case, cli, oracle_bin, corpus):
+def test_reference_golden_on_gpu(case, golden_results):
     if case['skip']:
         pytest.skip(case['skip'])
-    ok, out, err = golden_cases.run_case(case, cli, oracle_bin, corpus)
+    r = golden_results[case['id']]
+    if isinstance(r, Exception):
+        raise r
+    ok, out, err = r
     if not ok and b'not available on the device path' in err:
         pytest.skip('--output-extra/QNAME/mods: host-string columns not on the device path yet')
     assert ok, f"{case['cmd']}\nstderr: {err[-400:]!r}\nstdout head: {out[:300]!r}"
