@@ -10,6 +10,8 @@
  *   bam_mplp_init / bam_mplp_init_overlaps / bam_mplp_set_maxcnt /
  *   bam_mplp_auto / bam_mplp64_auto / bam_mplp_destroy            bam_plcmd.c:581-607,922; coverage.c:572-589,698; bedcov.c:303-316
  *   bam_plp_insertion                                             bam_plcmd.c:119 (via _mod), bam_tview.c:223,255
+ *   bam_plp_constructor / bam_plp_destructor / bam_mplp_constructor / bam_mplp_destructor      bam_plcmd.c:582-585, bedcov.c:313-314
+ *   bam_plp_next / bam_mplp_reset                                 phase.c:718, bam_plcmd.c (region restarts)
  *
  * Behaviour is htslib's: columns with n_plp > 0 in
  * (tid,pos) order, reads inside a column in push order, bam_pileup1_t fields
@@ -20,7 +22,10 @@
  * (b200_stage), obtains all (read, column) entries from the device
  * (b200_pileup_entries) and then hands the columns out one by one; `plp[i].b`
  * points at the iterator's copy of the read, valid until the next call, as in
- * htslib.  Constructor/destructor hooks (bam_plp_constructor) are not provided.
+ * htslib.  Constructor/destructor hooks: the constructor runs at bam_plp_push time for every mapped read (htslib
+ * skips reads its max-depth rule drops; here that rule is evaluated later, on the device, so such reads get a
+ * constructor AND a destructor call); destructors run when the reference sequence a read belongs to has been handed
+ * out, and for everything still buffered at bam_plp_reset / bam_plp_destroy.
  *
  * Link with -lb200pileup.  No CPU fallback: bam_plp_init() returns NULL when
  * no CUDA device is available.
@@ -28,6 +33,7 @@
 #ifndef B200_HTSLIB_COMPAT_H
 #define B200_HTSLIB_COMPAT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -90,18 +96,29 @@ int bam_plp_push(bam_plp_t iter, const bam1_t *b);   /* b == NULL marks end of i
 const bam_pileup1_t *bam_plp64_next(bam_plp_t iter, int *_tid, hts_pos_t *_pos, int *_n_plp);
 const bam_pileup1_t *bam_plp64_auto(bam_plp_t iter, int *_tid, hts_pos_t *_pos, int *_n_plp);
 const bam_pileup1_t *bam_plp_auto(bam_plp_t iter, int *_tid, int *_pos, int *_n_plp);
+const bam_pileup1_t *bam_plp_next(bam_plp_t iter, int *_tid, int *_pos, int *_n_plp);
 void bam_plp_set_maxcnt(bam_plp_t iter, int maxcnt);
+/* per-read client data (bam_pileup1_t.cd): func(data, b, cd) with the iterator's callback data */
+typedef int (*bam_plp_cd_f)(void *data, const bam1_t *b, bam_pileup_cd *cd);
+void bam_plp_constructor(bam_plp_t iter, bam_plp_cd_f func);
+void bam_plp_destructor(bam_plp_t iter, bam_plp_cd_f func);
 
 bam_mplp_t bam_mplp_init(int n, bam_plp_auto_f func, void **data);
 int bam_mplp_init_overlaps(bam_mplp_t iter);
 void bam_mplp_destroy(bam_mplp_t iter);
 void bam_mplp_set_maxcnt(bam_mplp_t iter, int maxcnt);
+void bam_mplp_reset(bam_mplp_t iter);
+void bam_mplp_constructor(bam_mplp_t iter, bam_plp_cd_f func);
+void bam_mplp_destructor(bam_mplp_t iter, bam_plp_cd_f func);
 int bam_mplp_auto(bam_mplp_t iter, int *_tid, int *_pos, int *n_plp, const bam_pileup1_t **plp);
 int bam_mplp64_auto(bam_mplp_t iter, int *_tid, hts_pos_t *_pos, int *n_plp, const bam_pileup1_t **plp);
 
 /* insertion sequence following a column with p->indel > 0 (bam_plp_insertion).  `ins` must hold at least
  * the returned length + 1 bytes (ins_cap); del_len receives the length of a deletion that follows. */
 int b200_plp_insertion(const bam_pileup1_t *p, char *ins, int ins_cap, int *del_len);
+/* htslib's own signature (kstring.h layout): ins->s is grown with realloc; returns the insertion length, -1 on failure */
+typedef struct kstring_t { size_t l, m; char *s; } kstring_t;
+int bam_plp_insertion(const bam_pileup1_t *p, kstring_t *ins, int *del_len);
 
 bam1_t *bam_init1(void);
 void bam_destroy1(bam1_t *b);

@@ -59,6 +59,8 @@ struct b200_plp {
     std::vector<bam1_t *> accum;           // reads of the contig being collected
     std::vector<bam1_t *> batch;           // reads of the contig being served
     bam1_t *pending = nullptr;             // first read of the next contig
+    std::vector<bam_pileup_cd> accum_cd, batch_cd; bam_pileup_cd pending_cd;   // client data of the same reads
+    bam_plp_cd_f construct = nullptr, destruct = nullptr;
     int last_tid = -1; hts_pos_t last_pos = -1;
     // served contig
     bool serving = false; int tid = -1; int64_t win_base = 0, n_cols = 0, col = 0, slab_beg = 0, slab_end = 0;
@@ -69,7 +71,20 @@ struct b200_plp {
     std::vector<int32_t> l_qseq, mtid; std::vector<uint32_t> n_cigar, cigar; std::vector<uint64_t> cigar_off, qual_off;
 };
 
-static void free_reads(std::vector<bam1_t *> &v) { for (bam1_t *b : v) bam_destroy1(b); v.clear(); }
+static void free_reads(b200_plp *it, std::vector<bam1_t *> &v, std::vector<bam_pileup_cd> &cd)
+{
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (it->destruct) it->destruct(it->data, v[i], &cd[i]);
+        bam_destroy1(v[i]);
+    }
+    v.clear(); cd.clear();
+}
+static void free_pending(b200_plp *it)
+{
+    if (!it->pending) return;
+    if (it->destruct) it->destruct(it->data, it->pending, &it->pending_cd);
+    bam_destroy1(it->pending); it->pending = nullptr;
+}
 
 static int stage_batch(b200_plp *it)
 {
@@ -149,7 +164,7 @@ static int load_slab(b200_plp *it)
 static const bam_pileup1_t *serve(b200_plp *it, int *_tid, hts_pos_t *_pos, int *_n)
 {
     while (it->serving) {
-        if (it->col >= it->n_cols) { it->serving = false; free_reads(it->batch); break; }
+        if (it->col >= it->n_cols) { it->serving = false; free_reads(it, it->batch, it->batch_cd); break; }
         if (it->col >= it->slab_end) { if (load_slab(it) != 0) { it->error = true; *_n = -1; return nullptr; } }
         while (it->col < it->slab_end) {
             const uint32_t n = it->col_n[(size_t)(it->col - it->slab_beg)];
@@ -160,7 +175,7 @@ static const bam_pileup1_t *serve(b200_plp *it, int *_tid, hts_pos_t *_pos, int 
                 const b200_pileup1_t &e = it->ents[it->ent_pos + k];
                 bam_pileup1_t &p = it->plp[k];
                 memset(&p, 0, sizeof p);
-                p.b = it->batch[(size_t)e.read]; p.qpos = e.qpos; p.indel = e.indel; p.cigar_ind = e.cigar_ind;
+                p.b = it->batch[(size_t)e.read]; p.cd = it->batch_cd[(size_t)e.read]; p.qpos = e.qpos; p.indel = e.indel; p.cigar_ind = e.cigar_ind;
                 p.is_del = e.is_del; p.is_head = e.is_head; p.is_tail = e.is_tail; p.is_refskip = e.is_refskip;
             }
             it->ent_pos += n;
@@ -174,8 +189,8 @@ static const bam_pileup1_t *serve(b200_plp *it, int *_tid, hts_pos_t *_pos, int 
 // the collected contig becomes the served one
 static int start_serving(b200_plp *it)
 {
-    it->batch.swap(it->accum);
-    it->accum.clear();
+    it->batch.swap(it->accum); it->batch_cd.swap(it->accum_cd);
+    it->accum.clear(); it->accum_cd.clear();
     if (it->batch.empty()) return 0;
     it->tid = it->batch[0]->core.tid;
     if (stage_batch(it) != 0) { it->error = true; return -1; }
@@ -199,20 +214,22 @@ bam_plp_t bam_plp_init(bam_plp_auto_f func, void *data)
 void bam_plp_destroy(bam_plp_t it)
 {
     if (!it) return;
-    free_reads(it->accum); free_reads(it->batch);
-    bam_destroy1(it->pending); bam_destroy1(it->tmp);
+    free_reads(it, it->accum, it->accum_cd); free_reads(it, it->batch, it->batch_cd);
+    free_pending(it); bam_destroy1(it->tmp);
     b200_engine_destroy(it->eng);
     delete it;
 }
 
 void bam_plp_reset(bam_plp_t it)
 {
-    free_reads(it->accum); free_reads(it->batch);
-    bam_destroy1(it->pending); it->pending = nullptr;
+    free_reads(it, it->accum, it->accum_cd); free_reads(it, it->batch, it->batch_cd);
+    free_pending(it);
     it->serving = false; it->eof = false; it->error = false; it->last_tid = -1; it->last_pos = -1;
 }
 
 void bam_plp_set_maxcnt(bam_plp_t it, int maxcnt) { it->maxcnt = maxcnt; }
+void bam_plp_constructor(bam_plp_t it, bam_plp_cd_f func) { it->construct = func; }
+void bam_plp_destructor(bam_plp_t it, bam_plp_cd_f func) { it->destruct = func; }
 
 int bam_plp_push(bam_plp_t it, const bam1_t *b)
 {
@@ -227,11 +244,16 @@ int bam_plp_push(bam_plp_t it, const bam1_t *b)
     it->last_tid = b->core.tid; it->last_pos = b->core.pos;
     bam1_t *c = bam_init1();
     if (!c || !bam_copy1(c, b)) { it->error = true; return -1; }
+    bam_pileup_cd cd; cd.i = 0;
     if (!it->accum.empty() && it->accum[0]->core.tid != c->core.tid) {
         // a new contig begins: it waits until the current one has been handed out
         if (it->pending) { it->error = true; bam_destroy1(c); return -1; }
-        it->pending = c;
-    } else it->accum.push_back(c);
+        if (it->construct) it->construct(it->data, c, &cd);
+        it->pending = c; it->pending_cd = cd;
+    } else {
+        if (it->construct) it->construct(it->data, c, &cd);
+        it->accum.push_back(c); it->accum_cd.push_back(cd);
+    }
     return 0;
 }
 
@@ -245,7 +267,7 @@ const bam_pileup1_t *bam_plp64_next(bam_plp_t it, int *_tid, hts_pos_t *_pos, in
         // a contig is complete when a read of another contig has arrived, or at end of input
         if (it->pending || (it->eof && !it->accum.empty())) {
             if (start_serving(it) != 0) { *_n = -1; return nullptr; }
-            if (it->pending) { it->accum.push_back(it->pending); it->pending = nullptr; }
+            if (it->pending) { it->accum.push_back(it->pending); it->accum_cd.push_back(it->pending_cd); it->pending = nullptr; }
             continue;
         }
         return nullptr;
@@ -268,6 +290,14 @@ const bam_pileup1_t *bam_plp64_auto(bam_plp_t it, int *_tid, hts_pos_t *_pos, in
             else { it->error = true; *_n = -1; return nullptr; }
         }
     }
+}
+
+const bam_pileup1_t *bam_plp_next(bam_plp_t it, int *_tid, int *_pos, int *_n)
+{
+    hts_pos_t p = 0;
+    const bam_pileup1_t *r = bam_plp64_next(it, _tid, &p, _n);
+    *_pos = p < INT_MAX ? (int)p : INT_MAX;
+    return r;
 }
 
 const bam_pileup1_t *bam_plp_auto(bam_plp_t it, int *_tid, int *_pos, int *_n)
@@ -305,6 +335,15 @@ bam_mplp_t bam_mplp_init(int n, bam_plp_auto_f func, void **data)
 int bam_mplp_init_overlaps(bam_mplp_t m) { for (b200_plp *p : m->it) p->overlaps = true; return 0; }
 void bam_mplp_set_maxcnt(bam_mplp_t m, int maxcnt) { for (b200_plp *p : m->it) p->maxcnt = maxcnt; }
 void bam_mplp_destroy(bam_mplp_t m) { if (!m) return; for (b200_plp *p : m->it) bam_plp_destroy(p); delete m; }
+void bam_mplp_constructor(bam_mplp_t m, bam_plp_cd_f func) { for (b200_plp *p : m->it) p->construct = func; }
+void bam_mplp_destructor(bam_mplp_t m, bam_plp_cd_f func) { for (b200_plp *p : m->it) p->destruct = func; }
+void bam_mplp_reset(bam_mplp_t m)
+{
+    for (b200_plp *p : m->it) bam_plp_reset(p);
+    std::fill(m->tid.begin(), m->tid.end(), (uint32_t)-1); std::fill(m->pos.begin(), m->pos.end(), (uint64_t)-1);
+    std::fill(m->n_plp.begin(), m->n_plp.end(), 0); std::fill(m->plp.begin(), m->plp.end(), nullptr);
+    m->min_tid = (uint32_t)-1; m->min_pos = (uint64_t)-1;
+}
 
 int bam_mplp64_auto(bam_mplp_t m, int *_tid, hts_pos_t *_pos, int *n_plp, const bam_pileup1_t **plp)
 {
@@ -361,6 +400,23 @@ int b200_plp_insertion(const bam_pileup1_t *p, char *ins, int cap, int *del_len)
         } else { if (op == 2 && del_len) *del_len = l; break; }
     }
     if (cap > 0) ins[n < cap ? n : cap - 1] = 0;
+    return n;
+}
+
+// htslib's signature: the kstring is grown as needed (bam_plp_insertion, sam.h)
+int bam_plp_insertion(const bam_pileup1_t *p, kstring_t *ins, int *del_len)
+{
+    if (!p || !ins) return -1;
+    int dl = 0;
+    const int n = b200_plp_insertion(p, nullptr, 0, &dl);          // length only
+    if (ins->m < (size_t)n + 1) {
+        char *t = (char *)realloc(ins->s, (size_t)n + 1);
+        if (!t) return -1;
+        ins->s = t; ins->m = (size_t)n + 1;
+    }
+    b200_plp_insertion(p, ins->s, (int)ins->m, &dl);
+    ins->s[n] = 0; ins->l = (size_t)n;
+    if (del_len) *del_len = dl;
     return n;
 }
 

@@ -323,5 +323,38 @@ int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b200_coverage
 int b200_glf(b200_engine_t *e, int32_t, int64_t *, int64_t *, int32_t *, float *, float *, size_t) { e->err = "emulation harness: GL not emulated"; return -1; }
 int b200_fetch_qual(b200_engine_t *e, uint8_t *q, size_t cap) { memcpy(q, e->qual.data(), std::min(cap, e->qual.size())); return 0; }
 int b200_fetch_mapq_keep(b200_engine_t *e, uint8_t *m, uint8_t *k, size_t n) { n = std::min(n, (size_t)e->b.n_reads); if (m) memcpy(m, e->mapq.data(), n); if (k) memcpy(k, e->state.data(), n); return 0; }
-int b200_pileup_entries(b200_engine_t *e, int32_t, int64_t, int64_t, uint32_t *, b200_pileup1_t *, size_t, size_t *) { e->err = "emulation harness: entries not emulated"; return -1; }
+// column-major (read, column) entries: the same per-column walk as k_entries_count / k_entries_fill (engine.cu)
+int b200_pileup_entries(b200_engine_t *e, int32_t file, int64_t beg, int64_t end, uint32_t *col_n, b200_pileup1_t *ents, size_t cap, size_t *n_out)
+{
+    if (!e->staged) { e->err = "no staged batch"; return -1; }
+    if (file < 0 || file >= e->b.n_files) { e->err = "bad file index"; return -1; }
+    View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);
+    int64_t rb = beg - e->win_base, re = end - e->win_base;
+    if (rb < 0) rb = 0;
+    if (re > v.ncols) re = v.ncols;
+    *n_out = 0;
+    if (re <= rb) return 0;
+    std::vector<b200_pileup1_t> all;
+    for (int64_t c64 = rb; c64 < re; ++c64) {
+        const int32_t c = (int32_t)c64;
+        const ReadRange rr = read_range(v, file, c >> 5);
+        uint32_t n = 0;
+        for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+            const int32_t i = range_at(rr, t_);
+            const ReadDesc d = v.desc[i];
+            if (c < d.rpos || c >= d.rend) continue;
+            Ent en; resolve(v, d, c, en);
+            if (en.k < 0) { const uint32_t *cg = v.cigar + d.cig_off; int k = 0; while (!is_mop(cg[k] & 0xf)) ++k; en.k = k; }
+            b200_pileup1_t p; memset(&p, 0, sizeof p);
+            p.read = i; p.qpos = en.qpos; p.indel = en.indel; p.cigar_ind = en.k;
+            p.is_del = en.is_del; p.is_head = en.is_head; p.is_tail = en.is_tail; p.is_refskip = en.is_refskip;
+            all.push_back(p); ++n;
+        }
+        col_n[c64 - rb] = n;
+    }
+    *n_out = all.size();
+    if (all.size() > cap) { e->err = "entry buffer too small"; return -2; }
+    if (!all.empty()) memcpy(ents, all.data(), all.size() * sizeof(b200_pileup1_t));
+    return 0;
+}
 }

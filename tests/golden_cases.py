@@ -122,3 +122,14 @@ def run_case(case, tool, view_tool, root, timeout=300):
     if case['kind'] == 'F':
         ok = not ok
     return ok, out, r.stderr
+
+
+# htslib-compatible iterator tier (T1): plp_dump client vs the oracle's `pileup-dump` (same lists for the CUDA engine and the
+# emulation harness)
+COMPAT_CASES = [
+    ([], ['test/mpileup/mp_DI.sam']), ([], ['test/mpileup/mp_P.sam']), ([], ['test/mpileup/mp_N2.sam']),
+    (['-o'], ['test/mpileup/overlap50.sam']), ([], ['test/mpileup/mpileup.1.bam']), (['-o'], ['test/mpileup/mpileup.1.bam']),
+    ([], ['test/mpileup/xx#depth1.sam', 'test/mpileup/xx#depth2.sam']), (['-d', '8500'], ['test/mpileup/deep.sam']),
+    ([], ['test/dat/mpileup.1.sam', 'test/dat/mpileup.2.sam', 'test/dat/mpileup.3.sam']),
+]
+COMPAT_IDS = ['DI', 'P', 'N2', 'overlap50', 'mpileup1', 'mpileup1-overlaps', 'two-files', 'maxcnt8500', 'three-files']

@@ -1,0 +1,35 @@
+"""The htslib-compatible iterator tier (samtools_b200/csrc/host/plp_compat.cpp) on the emulation harness: the host logic of
+bam_plp_* / bam_mplp_* (contig buffering, k-way merge, slab paging, hooks) against the oracle's restatement of htslib's
+iterator, without a GPU.  The same cases run on the CUDA engine in tests/test_gpu_parity.py::test_htslib_compat_iterator."""
+import os, subprocess
+import pytest
+import golden_cases
+from conftest import ROOT
+
+
+@pytest.fixture(scope='module')
+def dump_emul():
+    subprocess.run([os.path.join(ROOT, 'tests', 'emul', 'build.sh')], check=True)
+    return os.path.join(ROOT, 'tests', 'emul', '_build', 'plp_dump_emul')
+
+
+@pytest.mark.parametrize('args,files', golden_cases.COMPAT_CASES, ids=golden_cases.COMPAT_IDS)
+def test_iterator_tier_host_logic(args, files, dump_emul, oracle_bin, corpus):
+    paths = [os.path.join(corpus, f) for f in files]
+    got = subprocess.run([dump_emul, *args, *paths], capture_output=True)
+    want = subprocess.run([oracle_bin, 'pileup-dump', *args, *paths], capture_output=True)
+    assert got.returncode == 0, got.stderr[-300:]
+    assert got.stdout == want.stdout
+    assert len(got.stdout) > 100
+
+
+@pytest.mark.parametrize('args,files', golden_cases.COMPAT_CASES[:7], ids=golden_cases.COMPAT_IDS[:7])
+def test_iterator_hooks_and_kstring_insertion(args, files, dump_emul, oracle_bin, corpus):
+    """-c: constructor/destructor hooks (client data carried by every entry, one destructor call per constructed read)
+    and htslib's kstring signature of bam_plp_insertion; the dump itself must not change."""
+    paths = [os.path.join(corpus, f) for f in files]
+    got = subprocess.run([dump_emul, '-c', *args, *paths], capture_output=True)
+    want = subprocess.run([oracle_bin, 'pileup-dump', *args, *paths], capture_output=True)
+    assert got.returncode == 0, got.stderr[-300:]
+    assert got.stdout == want.stdout
+    assert b'hooks: ctor=' in got.stderr and b'bad=0' in got.stderr

@@ -206,12 +206,7 @@ def test_c2_size_properties():
 COMPAT = os.path.join(ROOT, 'tests', 'compat', '_build', 'plp_dump')
 
 
-@pytest.mark.parametrize('args,files', [
-    ([], ['test/mpileup/mp_DI.sam']), ([], ['test/mpileup/mp_P.sam']), ([], ['test/mpileup/mp_N2.sam']),
-    (['-o'], ['test/mpileup/overlap50.sam']), ([], ['test/mpileup/mpileup.1.bam']), (['-o'], ['test/mpileup/mpileup.1.bam']),
-    ([], ['test/mpileup/xx#depth1.sam', 'test/mpileup/xx#depth2.sam']), (['-d', '8500'], ['test/mpileup/deep.sam']),
-    ([], ['test/dat/mpileup.1.sam', 'test/dat/mpileup.2.sam', 'test/dat/mpileup.3.sam']),
-], ids=['DI', 'P', 'N2', 'overlap50', 'mpileup1', 'mpileup1-overlaps', 'two-files', 'maxcnt8500', 'three-files'])
+@pytest.mark.parametrize('args,files', golden_cases.COMPAT_CASES, ids=golden_cases.COMPAT_IDS)
 def test_htslib_compat_iterator(args, files, oracle_bin, corpus):
     """bam_mplp64_auto() through the GPU engine == the oracle's restatement of htslib's iterator,
     field by field (qpos, indel, is_del/head/tail/refskip, cigar_ind, quality seen through p->b, insertion text)."""
@@ -222,6 +217,15 @@ def test_htslib_compat_iterator(args, files, oracle_bin, corpus):
     assert got.returncode == 0, got.stderr[-300:]
     assert got.stdout == want.stdout
     assert len(got.stdout) > 100
+
+
+def test_htslib_compat_hooks(oracle_bin, corpus):
+    """constructor/destructor hooks + kstring bam_plp_insertion through the CUDA engine (host logic also in tests/test_emul_compat.py)"""
+    paths = [os.path.join(corpus, 'test/mpileup/mp_DI.sam')]
+    got = subprocess.run([COMPAT, '-c', *paths], capture_output=True)
+    want = subprocess.run([oracle_bin, 'pileup-dump', *paths], capture_output=True)
+    assert got.returncode == 0, got.stderr[-300:]
+    assert got.stdout == want.stdout and b'bad=0' in got.stderr
 
 
 # ---------------------------------------------------------------- BASELINE config 1 (examples/ex1): engine vs oracle
