@@ -2,8 +2,7 @@
 // Written the way an htslib user writes a pileup loop (cf. coverage.c:572-589): a pull callback
 // fills bam1_t records, bam_mplp64_auto() hands out columns.  Prints every bam_pileup1_t field so the
 // test can diff it against the CPU oracle's iterator (`plp_oracle pileup-dump`).
-#include "b200_htslib_compat.h"
-#include "../../samtools_b200/csrc/host/hts_io.hpp"
+#include "fill_bam1.hpp"
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
@@ -14,31 +13,6 @@
 static long n_ctor = 0, n_dtor = 0, cd_bad = 0;
 static int ctor(void *, const bam1_t *, bam_pileup_cd *cd) { cd->i = ++n_ctor; return 0; }
 static int dtor(void *, const bam1_t *, bam_pileup_cd *cd) { if (cd->i < 1 || cd->i > n_ctor) ++cd_bad; cd->i = -1; ++n_dtor; return 0; }
-
-struct Src { std::unique_ptr<b200::AlnReader> rd; };
-
-static int pull(void *data, bam1_t *b)
-{
-    Src *s = (Src *)data;
-    b200::Record r;
-    int ret = s->rd->next(r);
-    if (ret < 0) return ret;
-    const size_t lq = r.qname.size() + 1, l_qname = (lq + 3) & ~(size_t)3;
-    const size_t need = l_qname + 4 * r.cigar.size() + r.seq4.size() + r.qual.size() + r.aux.size();
-    if (b->m_data < need) { b->data = (uint8_t *)realloc(b->data, need); b->m_data = (uint32_t)need; }
-    memset(b->data, 0, l_qname);
-    memcpy(b->data, r.qname.c_str(), lq);
-    uint8_t *p = b->data + l_qname;
-    memcpy(p, r.cigar.data(), 4 * r.cigar.size()); p += 4 * r.cigar.size();
-    memcpy(p, r.seq4.data(), r.seq4.size()); p += r.seq4.size();
-    memcpy(p, r.qual.data(), r.qual.size()); p += r.qual.size();
-    memcpy(p, r.aux.data(), r.aux.size());
-    b->l_data = (int)need;
-    b->core.pos = r.pos; b->core.tid = r.tid; b->core.qual = r.mapq; b->core.flag = r.flag; b->core.l_qname = (uint16_t)l_qname;
-    b->core.l_extranul = (uint8_t)(l_qname - lq); b->core.n_cigar = (uint32_t)r.cigar.size(); b->core.l_qseq = r.l_qseq;
-    b->core.mtid = r.mtid; b->core.mpos = r.mpos; b->core.isize = r.isize;
-    return 0;
-}
 
 int main(int argc, char **argv)
 {

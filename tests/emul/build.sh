@@ -8,3 +8,11 @@ g++ -std=c++17 -O1 -g -ffp-contract=off -Wall -Wno-unused-function -o tests/emul
 # the htslib-compatible iterator tier (plp_compat.cpp) + its test client, on the emulation harness
 g++ -std=c++17 -O1 -g -ffp-contract=off -Wall -Wno-unused-function -Iinclude -o tests/emul/_build/plp_dump_emul \
     tests/compat/plp_dump.cpp samtools_b200/csrc/host/plp_compat.cpp samtools_b200/csrc/host/hts_io.cpp tests/emul/emul_engine.cpp -lz
+# the reference's own bam_plbuf layer, compiled UNMODIFIED where it lies (only in the dev container: /root/reference does
+# not travel) against tests/compat/shim/htslib/sam.h -> include/b200_htslib_compat.h; outputs stay under _build/
+REF=${B200_REFERENCE_DIR:-/root/reference}
+if [ -f "$REF/bam_plbuf.c" ]; then
+    gcc -c -O1 -Itests/compat/shim -Iinclude -I"$REF" -o tests/emul/_build/ref_bam_plbuf.o "$REF/bam_plbuf.c"
+    g++ -std=c++17 -O1 -g -Iinclude -Itests/compat/shim -I"$REF" -o tests/emul/_build/plbuf_dump_emul tests/compat/plbuf_dump.cpp \
+        tests/emul/_build/ref_bam_plbuf.o samtools_b200/csrc/host/plp_compat.cpp samtools_b200/csrc/host/hts_io.cpp tests/emul/emul_engine.cpp -lz
+fi
