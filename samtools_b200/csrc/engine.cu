@@ -741,7 +741,6 @@ extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_st
     if (b->n_files < 1) { snprintf(e->err, sizeof e->err, "n_files < 1"); return -1; }
     if (n >= (1LL << 31)) { snprintf(e->err, sizeof e->err, "batch too large (%lld reads)", (long long)n); return -1; }
     if (b->qual_bytes >= (1ULL << 32) || b->n_cigar_total >= (1ULL << 32)) { snprintf(e->err, sizeof e->err, "batch payload exceeds 4 GiB: split the window"); return -1; }
-    for (int64_t i = 0; i < 0; ++i) {}
     CK(cudaEventRecord(e->ev0, e->stream));
     e->n = n; e->n_files = b->n_files; e->tid = b->tid; e->tid_len = b->tid_len;
     e->name = b->tid_name ? b->tid_name : "";
