@@ -13,7 +13,7 @@ from samtools_b200 import synth
 def main():
     mb = float(sys.argv[1]) if len(sys.argv) > 1 else 2.0
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    cli = os.path.join(ROOT, 'samtools_b200', 'bin', 'b200samtools')
+    cli = os.environ.get('B200_TEST_CLI') or os.path.join(ROOT, 'samtools_b200', 'bin', 'b200samtools')
     oracle = os.path.join(ROOT, 'oracle', '_build', 'plp_oracle')
     ncols = int(mb * 1e6)
     soa = synth.make_region(ncols, seed=2)
