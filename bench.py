@@ -1,25 +1,33 @@
 #!/usr/bin/env python3
-"""bench.py -- mpileup reference positions/sec on the BASELINE C2-shape workload.
+"""bench.py -- mpileup reference positions/sec on the BASELINE workloads.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--region-mb M]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--region-mb M] [--modes a,b,...]
   (N>1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
 
-A "step" is one pass of the hot path over one staged batch: a 30x / 150 bp
-paired-read window of M Mb (default 8 Mb = 1.6 M reads, ~0.41 GB of SoA input
-and ~0.66 GB of pileup text, both far larger than the 126 MB L2, so successive
-steps cannot be served from cache), `mpileup -a` semantics without a FASTA
-(BASELINE.json configs[1] scaled up so one step lasts milliseconds, not
-microseconds).  With N GPUs every rank owns its own M-Mb region (weak scaling,
-no data-path collective; the per-step collective is the all_gather of the
-per-region column summaries rank 0 needs to emit shards in genome order).
+ONE JSON line.  Its top-level keys are the headline workload; `modes` holds one sub-record per further
+BASELINE configuration, each with its own value / roofline / cpu_baseline:
 
-value  device-resident: inputs already staged in HBM, K column-stage launches,
-       wall time between two device synchronisations (max over ranks).
-e2e    through the C ABI with HOST buffers: pinned-host SoA -> b200_stage (H2D +
-       read stage) -> b200_mpileup_text -> pinned-host text (D2H), every step.
-roofline  algorithmic bytes / CUDA-event time of the k_mpileup launch.
-cpu_baseline / --impl reference: the CPU oracle (the reference cannot be built
-       here: htslib is absent) on the box's host cores.
+  (headline)     BASELINE config 2 shape x8: M Mb (default 8), 30x, 150 bp pairs, `mpileup -a`, no FASTA -> no BAQ
+  mpileup_f_baq  the same window with its FASTA: `mpileup -f` = BAQ on every read (config 3's mode; bam_plcmd.c:1086,451)
+  depth_a        `depth -a` over the same window                                     (config 5; bam2depth.c:209-477)
+  coverage       `coverage` over the same window                                     (config 5; coverage.c:589-661)
+  gl_c4          config 4 shape: 500 x 2 kb targets at 200x + 20 hotspots at 2000x -> genotype likelihoods per column
+                 (bcf_call_glfgen + errmod_cal, bam2bcf.c:65-123)
+
+A "step" is one pass of the hot path over one staged batch; inputs (0.05 GB/Mb) and outputs (0.08 GB/Mb) of a
+step are far larger than the 126 MB L2, so successive steps cannot be served from cache.  With N GPUs every
+rank owns its own region (weak scaling, no data-path collective; the one collective is the all_gather of the
+per-region column summaries rank 0 needs to emit shards in genome order, issued once for all timed steps).
+
+value  device-resident: inputs already staged in HBM; K x (read stage + column stage), max over ranks.
+e2e    through the C ABI with HOST buffers: pinned-host SoA -> b200_stage (H2D + read stage) ->
+       b200_mpileup_text -> pinned-host text (D2H), every step.
+roofline  algorithmic bytes / CUDA-event time of the dominant kernel; BAQ: algorithmic non-fused
+       FP64 operations (l_qseq x (2bw+1) x 53 per read) / CUDA-event time of the BAQ kernels.
+cpu_baseline / --impl reference: the CPU oracle (the reference cannot be built here: htslib is absent,
+       DESIGN.md) on the box's host cores -- as many processes as the scheduler affinity AND the cgroup CPU
+       quota allow; the per-process and the single-process rates are reported next to the total so that a
+       starved box is visible.
 """
 import argparse
 import json
@@ -36,6 +44,10 @@ import numpy as np  # noqa: E402
 
 METRIC = 'mpileup reference positions/sec'
 UNIT = 'positions/s'
+ALL_MODES = ('mpileup_f_baq', 'depth_a', 'coverage', 'gl_c4')
+# nominal non-fused FP64 rate of a B200: 148 SMs x 64 FP64 lanes x 1.965 GHz (an FMA counts as ONE issue slot here
+# because BAQ must not contract a*b+c); no driver-measured figure exists for this pipe
+FP64_NONFMA_PEAK = 148 * 64 * 1.965e9
 
 
 def peaks():
@@ -43,6 +55,29 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def usable_cores():
+    """CPUs this process may really use: scheduler affinity capped by the cgroup CPU quota."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except AttributeError:
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()[:2]          # cgroup v2
+        if q != 'max':
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())       # cgroup v1
+            per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    n = aff if quota is None else max(1, min(aff, int(quota)))
+    return n, {'os_cpu_count': os.cpu_count(), 'sched_affinity': aff, 'cgroup_quota_cpus': quota}
 
 
 class ClockSampler:
@@ -95,6 +130,7 @@ class ClockSampler:
                 'samples': len(sm), 'source': 'nvml, polled during the timed regions'}
 
 
+# ------------------------------------------------------------------------------------------------ CPU arm
 def oracle_path():
     exe = os.path.join(ROOT, 'oracle', '_build', 'plp_oracle')
     if not os.path.exists(exe):
@@ -102,47 +138,104 @@ def oracle_path():
     return exe
 
 
-def cpu_sample(td, sample_mb):
-    """SAM text of a `sample_mb`-Mb window of the same workload shape (seeded)."""
+class CpuSample:
+    """A bounded sample of each workload for the CPU legs: a BGZF-compressed BAM (what `samtools mpileup` really reads,
+    so the CPU arm pays BGZF inflate + BAM decode like the real tool) plus its FASTA."""
+
+    def __init__(self, td, sample_mb=1.0):
+        from samtools_b200 import synth
+        self.td, self.mb = td, sample_mb
+        n = int(sample_mb * 1e6)
+        soa = synth.make_region(n, seed=99, chunk=500_000, with_ref=True)
+        self.bam = os.path.join(td, 'sample.bam'); self.fa = os.path.join(td, 'sample.fa')
+        synth.write_bam(self.bam, soa); synth.write_fasta(self.fa, soa['tid_name'], soa['ref_full'])
+        self.ncols = n
+        self.n_reads = len(soa['pos'])
+        self._panel = None
+
+    def panel(self):
+        if self._panel is None:
+            from samtools_b200 import synth
+            p = synth.make_panel(n_targets=25, n_hot=1, seed=98)
+            bam = os.path.join(self.td, 'panel.bam'); fa = os.path.join(self.td, 'panel.fa')
+            synth.write_bam(bam, p); synth.write_fasta(fa, p['tid_name'], p['ref_full'])
+            self._panel = (bam, fa, panel_columns(p))
+        return self._panel
+
+    def command(self, mode):
+        """(argv after the oracle binary, units of work per run, description)"""
+        if mode == 'mpileup_a':
+            return ['mpileup', '-a', self.bam], self.ncols, f'`mpileup -a` over a {self.mb:g} Mb 30x/150bp BAM window'
+        if mode == 'mpileup_f_baq':
+            return ['mpileup', '-a', '-f', self.fa, self.bam], self.ncols, f'`mpileup -a -f` (BAQ) over a {self.mb:g} Mb 30x/150bp BAM window'
+        if mode == 'depth_a':
+            return ['depth', '-a', self.bam], self.ncols, f'`depth -a` over a {self.mb:g} Mb 30x/150bp BAM window'
+        if mode == 'coverage':
+            return ['coverage', self.bam], self.ncols, f'`coverage` over a {self.mb:g} Mb 30x/150bp BAM window'
+        if mode == 'gl_c4':
+            bam, fa, ncol = self.panel()
+            return ['gl', '-B', '-f', fa, bam], ncol, 'genotype likelihoods (`gl -B -f`: glfgen + errmod_cal per column) over a 25-target 200x panel with one 2000x hotspot'
+        raise ValueError(mode)
+
+
+def panel_columns(p):
+    """covered columns of a panel batch (what the GL path emits one record for): union of the reads' reference spans"""
     from samtools_b200 import synth
-    n = int(sample_mb * 1e6)
-    soa = synth.make_region(n, seed=99, chunk=500_000)
-    sam = os.path.join(td, 'sample.sam')
-    synth.write_sam(sam, soa)
-    return sam, n
+    pos = p['pos']; end = pos + synth.ref_span(p)
+    hi = np.maximum.accumulate(end)
+    starts = np.concatenate([[True], pos[1:] > hi[:-1]])
+    seg_beg = pos[starts]
+    seg_end = np.concatenate([hi[:-1][starts[1:]], hi[-1:]])
+    return int((seg_end - seg_beg).sum())
 
 
-def run_oracle_parallel(exe, sam, procs):
+def run_oracle_parallel(exe, argv, procs):
     t0 = time.perf_counter()
-    ps = [subprocess.Popen([exe, 'mpileup', '-a', sam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for _ in range(procs)]
+    ps = [subprocess.Popen([exe] + argv, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for _ in range(procs)]
     for p in ps:
         if p.wait() != 0:
-            raise RuntimeError('oracle failed')
+            raise RuntimeError('oracle failed: ' + ' '.join(argv))
     return time.perf_counter() - t0
 
 
+def cpu_leg(exe, sample, mode, procs, reps, warm):
+    """`procs` concurrent single-threaded oracle processes (the reference pileup is single-threaded, bam_plcmd.c:1098; an
+    all-cores run is region-sharded processes), each over the whole sample; returns the cpu_baseline record."""
+    argv, units, what = sample.command(mode)
+    t1 = run_oracle_parallel(exe, argv, 1)                     # one process alone: the un-contended per-core rate
+    for _ in range(warm):
+        run_oracle_parallel(exe, argv, procs)
+    t = [run_oracle_parallel(exe, argv, procs) for _ in range(reps)]
+    total = sum(t)
+    val = procs * units * reps / total
+    return {'value': val, 'unit': UNIT, 'cores': procs, 'kind': 'port',
+            'per_process': val / procs, 'one_process_alone': units / t1, 'parallel_efficiency': (val / procs) / (units / t1),
+            'sample': f'{procs} concurrent single-threaded oracle processes, each {what} (BGZF inflate + BAM decode included) to /dev/null, '
+                      f'{reps} timed rounds', 'seconds_per_round': total / reps}, total / reps
+
+
 def reference_arm(args):
-    """--impl reference: the CPU implementation of the path on all host cores (oracle port)."""
+    """--impl reference: the CPU implementation of the path on all usable host cores (oracle port)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     exe = oracle_path()
-    cores = os.cpu_count() or 1
-    sample_mb = 1.0
+    cores, how = usable_cores()
+    modes = parse_modes(args)
     with tempfile.TemporaryDirectory() as td:
-        sam, ncols = cpu_sample(td, sample_mb)
-        for _ in range(max(args.warmup, 1) if args.warmup else 0):
-            run_oracle_parallel(exe, sam, cores)
-        t = [run_oracle_parallel(exe, sam, cores) for _ in range(args.steps)]
-    total = sum(t)
-    val = cores * ncols * args.steps / total
-    sample = f'{cores} concurrent single-threaded oracle processes (the reference pileup is single-threaded, bam_plcmd.c:1098), ' \
-             f'each `mpileup -a` over a {sample_mb:g} Mb 30x/150bp SAM-text window to /dev/null'
+        sample = CpuSample(td, 1.0)
+        head, sec = cpu_leg(exe, sample, 'mpileup_a', cores, args.steps, min(args.warmup, 1))
+        sub = {}
+        for m in modes:
+            rec, _ = cpu_leg(exe, sample, m, cores, 2, 0)
+            sub[m] = {'value': rec['value'], 'unit': UNIT, 'cpu_baseline': rec}
+    head['core_accounting'] = how
+    val = head['value']
     line = {'metric': METRIC, 'value': val, 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
+            'ms_per_step': 1e3 * sec, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
             'data': 'synthetic', 'config': workload_config(args),
-            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
-            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+            'cpu_baseline': head,
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0, 'modes': sub}
     print(json.dumps(line))
 
 
@@ -151,7 +244,20 @@ def workload_config(args):
                         f'`mpileup -a` (no FASTA -> no BAQ, overlap removal on, -Q13, -d 8000)',
             'region_mb_per_gpu': args.region_mb, 'depth': 30, 'read_len': 150,
             'l2_policy': 'inputs (0.05 GB/Mb) and outputs (0.08 GB/Mb) per step exceed the 126 MB L2; no explicit flush',
-            'parallelism': f'region-shard x{args.gpus}'}
+            'parallelism': f'region-shard x{args.gpus}',
+            'modes': 'sub-records: mpileup_f_baq (same window + FASTA, BAQ on), depth_a, coverage (same window), gl_c4 (200x panel with 2000x hotspots)'}
+
+
+def parse_modes(args):
+    if args.modes in ('', 'none'):
+        return []
+    if args.modes == 'all':
+        return list(ALL_MODES)
+    ms = [m for m in args.modes.split(',') if m]
+    for m in ms:
+        if m not in ALL_MODES:
+            raise SystemExit(f'unknown mode {m}; choose from {ALL_MODES}')
+    return ms
 
 
 def pin(soa):
@@ -173,6 +279,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--region-mb', type=float, default=8.0)
+    ap.add_argument('--modes', default='all', help="comma list of extra workloads (%s), 'all' or 'none'" % ', '.join(ALL_MODES))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-handles', type=int, default=3,
                     help='engine handles (one host thread each) used by the end-to-end loop; handles are per-thread objects like the htslib iterators they replace')
@@ -192,10 +299,12 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
+    modes = parse_modes(args)
 
     ncols = int(args.region_mb * 1e6)
-    soa = synth.make_region(ncols, seed=2 + rank)          # this rank's region
-    soa['ref'] = None
+    soa_ref = synth.make_region(ncols, seed=2 + rank, with_ref=True)          # this rank's region
+    ref_arr = soa_ref['ref']
+    soa = dict(soa_ref); soa['ref'] = None
     soa = pin(soa)
     n_reads = len(soa['pos'])
     h2d = int(sum(soa[k].nbytes for k in ('pos', 'flag', 'mapq', 'l_qseq', 'n_cigar', 'cigar_off', 'qual_off', 'mtid', 'mpos', 'isize',
@@ -222,15 +331,23 @@ def main():
     eng_dev.set_keep_raw(True)
     eng_dev.stage(soa, sconf)
     stage_ms = []
+    summaries = []
 
     def step_device():
         """the whole hot path on resident inputs: read stage (filters, overlap tweak, descriptors, read slices) + column stage"""
         eng_dev.restage()
         stage_ms.append(eng_dev.last_stage_device_ms)
         n = eng_dev.mpileup_text(mconf, fetch=False)
-        if world > 1:   # column summaries of every region, for ordered emission at rank 0
-            shard.gather_summaries([n, ncols, n_reads], device=dev)
+        summaries.append([n, ncols, n_reads])
         return n
+
+    def exchange_summaries():
+        """the path's one collective: per-region column summaries (bytes, columns, reads) of every step to every rank, so
+        that rank 0 can emit the shards in genome order -- one all_gather for all the steps, not one per step"""
+        if world > 1 and summaries:
+            flat = [x for s in summaries for x in s]
+            shard.gather_summaries(flat, device=dev)
+        summaries.clear()
 
     # end-to-end: the caller owns a stream of windows; like htslib handles, an engine handle serves one
     # thread, so a pipeline uses one handle per host thread (H2D of one window overlaps kernels / D2H of another)
@@ -253,17 +370,15 @@ def main():
         def worker(j):
             for s_ in range(j, k_steps, n_h):
                 res[j] = one_window(handles[j], outs[j])
+                summaries.append([res[j], ncols, n_reads])
         ths = [_th.Thread(target=worker, args=(j,)) for j in range(n_h)]
         [t.start() for t in ths]; [t.join() for t in ths]
-        if world > 1:
-            shard.gather_summaries([max(res), ncols, n_reads], device=dev)
+        exchange_summaries()
         return max(res)
 
-    def step_e2e():
-        return run_e2e(n_h)
-
     for _ in range(args.warmup):
-        step_e2e(); step_device()
+        run_e2e(n_h); step_device()
+    exchange_summaries()
 
     # ---- device-resident: K passes of read stage + column stage
     kernel_ms, parts_ms = [], []
@@ -276,6 +391,7 @@ def main():
             step_device()
             kernel_ms.append(eng_dev.last_kernel_ms)
             parts_ms.append(eng_dev.last_mpileup_parts_ms)
+        exchange_summaries()
         sync_all()
         dt = time.perf_counter() - t0
         launches = eng_dev.launches - l0
@@ -287,9 +403,12 @@ def main():
         dt_e2e = time.perf_counter() - t0
     dt = shard.max_over_ranks(dt, dev); dt_e2e = shard.max_over_ranks(dt_e2e, dev)
     clocks = clk.summary()
+    for h in handles[1:]:
+        h.close()
 
+    peak, peak_src = peaks()
+    line = None
     if rank == 0:
-        peak, peak_src = peaks()
         kms = float(np.mean(kernel_ms))
         size_ms, scan_ms, write_ms = [float(x) for x in np.mean(np.array(parts_ms), axis=0)]
         # dominant kernel = the write pass: it re-reads every staged read (descriptor, qualities, bases) and
@@ -297,11 +416,11 @@ def main():
         alg = bytes_in + out_len
         achieved = alg / (write_ms * 1e-3) / 1e9
         traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             if abs(tj.get('region_mb', 0) - args.region_mb) < 1e-9:
-                traffic = tj.get('k_mpileup_write_dram_bytes')
+                traffic = tj.get('write_kernel_dram_bytes')
         value = world * ncols * args.steps / dt
         e2e = world * ncols * args.steps / dt_e2e
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -310,28 +429,130 @@ def main():
                 'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(out_len), 'ms_per_step': 1e3 * dt_e2e / args.steps,
                         'handles': n_h},
                 'gpu_launches': int(launches),
-                'roofline': {'bound': 'hbm', 'kernel': 'k_mpileup_write', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'roofline': {'bound': 'hbm', 'kernel': 'mpileup write pass', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(alg),
                              'bytes_in': int(bytes_in), 'bytes_out': int(out_len), 'kernel_ms': write_ms,
-                             'step_kernels_ms': {'read_stage(k_prep*,k_build_desc,k_overlap,ranges; includes its host syncs)': float(np.mean(stage_ms)),
-                                                 'size_pass(k_ss_reads+k_ss_scan+k_ss_cols)': size_ms, 'k_scan_u32_to_u64': scan_ms, 'k_mpileup_write': write_ms,
-                                                 'column_stage_total': kms, 'total': kms + float(np.mean(stage_ms))},
+                             'step_kernels_ms': {'read_stage': float(np.mean(stage_ms)), 'size_pass': size_ms, 'tile_offset_scan': scan_ms,
+                                                 'write_pass': write_ms, 'column_stage_total': kms, 'total': kms + float(np.mean(stage_ms))},
                              'step_frac': alg / ((kms + float(np.mean(stage_ms))) * 1e-3) / 1e9 / peak},
                 'reads_per_step_per_gpu': n_reads}
+
+    # ------------------------------------------------------------------------------------ further BASELINE configurations
+    sub = {}
+    msteps = max(3, min(args.steps, 10))
+
+    def timed(fn, k, w=2):
+        for _ in range(w):
+            fn()
+        sync_all()
+        t0_ = time.perf_counter()
+        for _ in range(k):
+            fn()
+        sync_all()
+        return shard.max_over_ranks(time.perf_counter() - t0_, dev)
+
+    if 'mpileup_f_baq' in modes:
+        soa_b = dict(soa); soa_b['ref'] = ref_arr
+        e = engine.Engine(local); e.set_keep_raw(True)
+        bconf = engine.default_stage_conf(engine.MODE_MPILEUP)
+        e.stage(soa_b, bconf)
+        blen = e.mpileup_text(mconf, fetch=False)
+        baq_ms, st_ms, k_ms = [], [], []
+
+        def step_baq():
+            e.restage(); baq_ms.append(e.last_baq_ms); st_ms.append(e.last_stage_device_ms)
+            e.mpileup_text(mconf, fetch=False); k_ms.append(e.last_kernel_ms)
+        dtb = timed(step_baq, msteps, w=1)
+        l = soa['l_qseq'].astype(np.int64)
+        ops = float((l * 15 * 53).sum())                       # l_qseq x (2bw+1) x (fwd 22 + bwd 25 + MAP 6), bw = 7
+        bms = float(np.mean(baq_ms[-msteps:]))
+        ach = ops / (bms * 1e-3)
+        sub['mpileup_f_baq'] = {
+            'workload': f'same {args.region_mb:g} Mb window with its FASTA: `mpileup -a -f` (BAQ = sam_prob_realn on every read, overlap removal, -Q13)',
+            'value': world * ncols * msteps / dtb, 'unit': UNIT, 'ms_per_step': 1e3 * dtb / msteps, 'steps': msteps, 'bytes_out': int(blen),
+            'reads_per_s_baq_kernels': n_reads / (bms * 1e-3),
+            'roofline': {'bound': 'fp64 (non-fused: BAQ must not contract a*b+c)', 'kernel': 'BAQ kernels (k_baq_plan + k_baq_*)', 'achieved': ach / 1e12,
+                         'peak': FP64_NONFMA_PEAK / 1e12, 'unit': 'Top/s (FP64, non-FMA)', 'frac': ach / FP64_NONFMA_PEAK,
+                         'peak_source': 'nominal: 148 SMs x 64 FP64 lanes x 1.965 GHz (no measured FP64 figure in MEASURED_PEAKS.json)',
+                         'algorithmic_ops_per_launch': ops, 'kernel_ms': bms, 'traffic': None,
+                         'step_kernels_ms': {'read_stage_total': float(np.mean(st_ms[-msteps:])), 'of_which_baq': bms, 'column_stage': float(np.mean(k_ms[-msteps:]))}}}
+        e.close()
+
+    if 'depth_a' in modes or 'coverage' in modes:
+        e = engine.Engine(local); e.set_keep_raw(True)
+        if 'depth_a' in modes:
+            dconf = engine.default_stage_conf(engine.MODE_DEPTH)
+            e.stage(soa, dconf)
+            dlen = e.depth_text(all=1, fetch=False)
+            k_ms, st_ms = [], []
+
+            def step_depth():
+                e.restage(); st_ms.append(e.last_stage_device_ms)
+                e.depth_text(all=1, fetch=False); k_ms.append(e.last_kernel_ms)
+            dtd = timed(step_depth, msteps)
+            din = int((4 * soa['n_cigar'].astype(np.int64) + 24).sum())          # depth needs no bases / qualities at -q 0
+            kd = float(np.mean(k_ms[-msteps:]))
+            sub['depth_a'] = {'workload': f'`depth -a` over the same {args.region_mb:g} Mb window (BASELINE config 5)',
+                              'value': world * ncols * msteps / dtd, 'unit': UNIT, 'ms_per_step': 1e3 * dtd / msteps, 'steps': msteps, 'bytes_out': int(dlen),
+                              'roofline': {'bound': 'hbm', 'kernel': 'k_depth_size + scan + k_depth_write', 'achieved': (din + dlen) / (kd * 1e-3) / 1e9, 'peak': peak,
+                                           'unit': 'GB/s', 'frac': (din + dlen) / (kd * 1e-3) / 1e9 / peak, 'peak_source': peak_src,
+                                           'algorithmic_bytes_per_launch': int(din + dlen), 'kernel_ms': kd, 'traffic': None,
+                                           'step_kernels_ms': {'read_stage': float(np.mean(st_ms[-msteps:])), 'column_stage': kd}}}
+        if 'coverage' in modes:
+            cconf = engine.default_stage_conf(engine.MODE_COVERAGE, rflag_filter=4 | 256 | 512 | 1024, end=ncols)
+            e.stage(soa, cconf)
+            k_ms, st_ms = [], []
+
+            def step_cov():
+                e.restage(); st_ms.append(e.last_stage_device_ms)
+                e.coverage(min_baseQ=0, min_depth=1); k_ms.append(e.last_kernel_ms)
+            dtc = timed(step_cov, msteps)
+            cin = int((soa['l_qseq'].astype(np.int64) + 4 * soa['n_cigar'].astype(np.int64) + 24).sum())   # qualities + cigar + core fields
+            kc = float(np.mean(k_ms[-msteps:]))
+            sub['coverage'] = {'workload': f'`coverage` over the same {args.region_mb:g} Mb window (BASELINE config 5)',
+                               'value': world * ncols * msteps / dtc, 'unit': UNIT, 'ms_per_step': 1e3 * dtc / msteps, 'steps': msteps,
+                               'roofline': {'bound': 'hbm', 'kernel': 'k_coverage', 'achieved': cin / (kc * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                            'frac': cin / (kc * 1e-3) / 1e9 / peak, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': cin, 'kernel_ms': kc,
+                                            'traffic': None, 'step_kernels_ms': {'read_stage': float(np.mean(st_ms[-msteps:])), 'column_stage': kc}}}
+        e.close()
+
+    if 'gl_c4' in modes:
+        panel = synth.make_panel(seed=4 + rank)                   # 500 x 2 kb at 200x, 20 hotspots at 2000x
+        pcols = panel_columns(panel)
+        pp = pin(panel)
+        e = engine.Engine(local); e.set_keep_raw(True)
+        gconf = engine.default_stage_conf(engine.MODE_MPILEUP, baq=0)
+        e.stage(pp, gconf)
+        k_ms, st_ms = [], []
+
+        def step_gl():
+            e.restage(); st_ms.append(e.last_stage_device_ms)
+            e.glf(13, 0, fetch=False); k_ms.append(e.last_kernel_ms)
+        dtg = timed(step_gl, msteps, w=1)
+        gin = synth.algorithmic_bytes_in(panel, overlap=True)
+        gout = pcols * (25 * 4 + 16)
+        kg = float(np.mean(k_ms[-msteps:]))
+        sub['gl_c4'] = {'workload': 'BASELINE config 4 shape: 500 targets x 2 kb at 200x, 20 hotspots at 2000x (%d reads, %d covered columns), '
+                                    '`mpileup -B` read stage -> bcf_call_glfgen + errmod_cal per column, likelihoods left in HBM' % (len(panel['pos']), pcols),
+                        'value': world * pcols * msteps / dtg, 'unit': 'columns/s', 'ms_per_step': 1e3 * dtg / msteps, 'steps': msteps,
+                        'roofline': {'bound': 'hbm', 'kernel': 'k_gl_count + scan + k_gl', 'achieved': (gin + gout) / (kg * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                     'frac': (gin + gout) / (kg * 1e-3) / 1e9 / peak, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(gin + gout),
+                                     'kernel_ms': kg, 'traffic': None, 'step_kernels_ms': {'read_stage': float(np.mean(st_ms[-msteps:])), 'column_stage': kg}}}
+        e.close()
+
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             exe = oracle_path()
             with tempfile.TemporaryDirectory() as td:
-                sam, nc = cpu_sample(td, 2.0)
-                reps = 4
-                t0 = time.perf_counter()
-                for _ in range(reps):
-                    subprocess.run([exe, 'mpileup', '-a', sam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
-                cpu_dt = time.perf_counter() - t0
-            line['cpu_baseline'] = {'value': reps * nc / cpu_dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-                                    'sample': f'{reps} x CPU oracle `mpileup -a` over a 2 Mb 30x/150bp SAM-text window (same generator), 1 thread'}
+                sample = CpuSample(td, 1.0)
+                rec, _ = cpu_leg(exe, sample, 'mpileup_a', 1, 4, 0)
+                line['cpu_baseline'] = rec
+                for m in sub:
+                    rec, _ = cpu_leg(exe, sample, m, 1, 1, 0)
+                    sub[m]['cpu_baseline'] = rec
+        line['modes'] = sub
         print(json.dumps(line))
-    for h in handles:
-        h.close()
+    eng.close(); eng_dev.close()
     if world > 1:
         dist.destroy_process_group()
 

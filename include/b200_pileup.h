@@ -179,7 +179,8 @@ int b200_stage(b200_engine_t *e, const b200_batch_t *batch, const b200_stage_con
 int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *conf, char *out, size_t out_cap, size_t *out_len);
 int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *conf, char *out, size_t out_cap, size_t *out_len);
 int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *conf, b200_coverage_sums_t *sums);
-/* genotype likelihoods per covered column and file: n, qsum[4], p[25] */
+/* genotype likelihoods per covered column and file: n, qsum[4], p[25].  col_pos == NULL: compute only, results stay in
+ * HBM (device-only timing, like out == NULL of the text calls); *n_cols is then the number of candidate columns */
 int b200_glf(b200_engine_t *e, int32_t min_baseQ, int64_t *n_cols, int64_t *col_pos, int32_t *n_bases,
              float *qsum, float *p25, size_t cap_cols);
 /* qualities after the read stage (BAQ / overlap tweak), for inspection and the iterator tier */
@@ -198,9 +199,13 @@ int b200_pileup_entries(b200_engine_t *e, int32_t file, int64_t beg, int64_t end
 int b200_set_keep_raw(b200_engine_t *e, int on);
 int b200_restage(b200_engine_t *e, b200_stage_stats_t *stats);
 double b200_last_stage_device_ms(const b200_engine_t *e);   /* device part of the last b200_stage / b200_restage */
+double b200_last_baq_ms(const b200_engine_t *e);            /* of which: the BAQ kernels (sam_prob_realn), 0 when BAQ did not run */
 double b200_last_kernel_ms(const b200_engine_t *e);
 double b200_last_stage_ms(const b200_engine_t *e);
 int64_t b200_launch_count(const b200_engine_t *e);   /* kernels launched by this handle so far */
+/* hts_drand48 draws consumed so far by b200_glf (errmod_cal shuffles a column's bases when it holds more than 255; the
+ * reference draws from ONE process-wide stream, so a region shard continues from its predecessor's count) */
+uint64_t b200_gl_rng_draws(const b200_engine_t *e);
 /* last b200_mpileup_text(): device time of its three launches -- sizing kernel, tile-offset scan, write kernel */
 void b200_last_mpileup_parts_ms(const b200_engine_t *e, double *ms3);
 

@@ -125,18 +125,18 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_s
 // (arithmetic in plp_stage.h; one thread per read)
 __device__ __forceinline__ void merge_acc(const StageAcc &a, StageAcc *g)
 {
-    unsigned long long v[7] = {a.n_kept, a.n_kept_in_window, a.sum_rlen, a.sum_indel_text, a.n_reads, a.n_selected, a.summed_mapq};
+    unsigned long long v[8] = {a.n_kept, a.n_kept_in_window, a.sum_rlen, a.sum_indel_text, a.n_reads, a.n_selected, a.summed_mapq, a.n_desc};
     int mx = a.max_rend;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        for (int k = 0; k < 8; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     if ((threadIdx.x & 31) == 0) {
-        unsigned long long *gp[7] = {&g->n_kept, &g->n_kept_in_window, &g->sum_rlen, &g->sum_indel_text, &g->n_reads, &g->n_selected, &g->summed_mapq};
+        unsigned long long *gp[8] = {&g->n_kept, &g->n_kept_in_window, &g->sum_rlen, &g->sum_indel_text, &g->n_reads, &g->n_selected, &g->summed_mapq, &g->n_desc};
 #pragma unroll
-        for (int k = 0; k < 7; ++k) if (v[k]) atomicAdd(gp[k], v[k]);
+        for (int k = 0; k < 8; ++k) if (v[k]) atomicAdd(gp[k], v[k]);
         if (mx != INT32_MIN) atomicMax(&g->max_rend, mx);
     }
 }
@@ -534,23 +534,23 @@ __global__ void __launch_bounds__(256) k_coverage(View v, int32_t min_baseQ, int
 }
 
 // column-major pileup entries for the iterator tier: counts, then entries
-__global__ void k_entries_count(View v, int f, uint32_t *col_n)
+__global__ void k_entries_count(View v, int f, int32_t c0, uint32_t *col_n)   // columns [c0, v.ncols); col_n[c - c0]
 {
-    const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int32_t c = c0 + (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= v.ncols) return;
     const int g = c >> 5;
     const ReadRange rr = read_range(v, f, g);
     uint32_t n = 0;
     for (int32_t t_ = 0; t_ < rr.n; ++t_) { const ReadDesc d = v.desc[range_at(rr, t_)]; if (c >= d.rpos && c < d.rend) ++n; }
-    col_n[c] = n;
+    col_n[c - c0] = n;
 }
-__global__ void k_entries_fill(View v, int f, const uint64_t *col_off, b200_pileup1_t *ents, int64_t file_first)
+__global__ void k_entries_fill(View v, int f, int32_t c0, const uint64_t *col_off, b200_pileup1_t *ents)
 {
-    const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int32_t c = c0 + (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= v.ncols) return;
     const int g = c >> 5;
     const ReadRange rr = read_range(v, f, g);
-    b200_pileup1_t *o = ents + col_off[c];
+    b200_pileup1_t *o = ents + col_off[c - c0];
     for (int32_t t_ = 0; t_ < rr.n; ++t_) {
         const int32_t i = range_at(rr, t_);
         const ReadDesc d = v.desc[i];
@@ -566,7 +566,6 @@ __global__ void k_entries_fill(View v, int f, const uint64_t *col_off, b200_pile
         p.is_del = e.is_del; p.is_head = e.is_head; p.is_tail = e.is_tail; p.is_refskip = e.is_refskip;
         *o++ = p;
     }
-    (void)file_first;
 }
 __global__ void k_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int32_t n, uint64_t *st, uint32_t *ticket)
 {
@@ -625,6 +624,7 @@ extern "C" const char *b200_last_error(const b200_engine_t *e) { return e ? e->e
 extern "C" double b200_last_kernel_ms(const b200_engine_t *e) { return e->last_kernel_ms; }
 extern "C" double b200_last_stage_ms(const b200_engine_t *e) { return e->last_stage_ms; }
 extern "C" int64_t b200_launch_count(const b200_engine_t *e) { return e->launches; }
+extern "C" uint64_t b200_gl_rng_draws(const b200_engine_t *e) { return e ? e->gl_rng_draws : 0; }
 extern "C" void b200_last_mpileup_parts_ms(const b200_engine_t *e, double *ms3) { for (int i = 0; i < 3; ++i) ms3[i] = e->last_parts_ms[i]; }
 
 extern "C" int b200_engine_create(int device, b200_engine_t **out)
@@ -646,6 +646,7 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
         return -1;
     }
     cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1); cudaEventCreate(&e->evA); cudaEventCreate(&e->evB);
+    cudaEventCreate(&e->evB0); cudaEventCreate(&e->evB1);
     cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device);
     e->smem_text = 24 * 1024;
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
@@ -682,6 +683,7 @@ extern "C" void b200_engine_destroy(b200_engine_t *e)
     e->free_all();
     cudaFree(e->d_acc); cudaFree(e->d_misc);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->evA); cudaEventDestroy(e->evB);
+    cudaEventDestroy(e->evB0); cudaEventDestroy(e->evB1);
     cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -732,6 +734,32 @@ __global__ void k_apply_maxdrop(const uint8_t *state, ReadDesc *desc, int32_t *e
 }
 
 static int stage_device(b200_engine *e, b200_stage_stats_t *stats);
+
+// Some record starts before its predecessor (rare path).  htslib's bam_plp_push rejects a PUSHED read that starts before
+// the previous pushed read of the same file ("The input is not sorted", error return); reads dropped by the filters never
+// reach the push.  The column kernels binary-search the descriptors by start, so unsorted input must not get through:
+// exact check over the kept reads of each file on the host.  depth (bam2depth.c:329-333) tolerates some disorder; here any
+// disorder among its kept reads is refused ("Data is not position sorted") rather than risking silently wrong counts.
+static int check_sorted_host(b200_engine *e, int64_t n)
+{
+    std::vector<ReadDesc> hd((size_t)n);
+    std::vector<uint8_t> st((size_t)n);
+    CK(cudaMemcpyAsync(hd.data(), e->desc, (size_t)n * sizeof(ReadDesc), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(st.data(), e->state, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int f = 0; f < e->n_files; ++f) {
+        bool have = false; int32_t last = 0;
+        for (int64_t i = e->h_file_start[f]; i < e->h_file_start[f + 1]; ++i) {
+            if (st[i] != ST_KEEP) continue;
+            if (have && hd[i].rpos < last) {
+                snprintf(e->err, sizeof e->err, "%s", e->sconf.mode == B200_MODE_DEPTH ? "Data is not position sorted" : "The input is not sorted (reads out of order)");
+                return -3;
+            }
+            have = true; last = hd[i].rpos;
+        }
+    }
+    return 0;
+}
 
 extern "C" int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t *cf, b200_stage_stats_t *stats)
 {
@@ -818,7 +846,13 @@ static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
     StageAcc *acc = (StageAcc *)e->d_acc;
     if (n > 0) {
         k_prep1<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, acc); e->launches++;
-        if (cf->mode == B200_MODE_MPILEUP && cf->baq && e->has_ref) { if (launch_baq(e, r, *cf)) return -1; }
+        e->baq_ran = false;
+        if (cf->mode == B200_MODE_MPILEUP && cf->baq && e->has_ref) {
+            CK(cudaEventRecord(e->evB0, e->stream));
+            if (launch_baq(e, r, *cf)) return -1;
+            CK(cudaEventRecord(e->evB1, e->stream));
+            e->baq_ran = true;
+        }
         k_prep2<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state); e->launches++;
         k_build_desc<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, e->desc, e->endv, acc, e->win_base, e->cig_x, e->cig_y); e->launches++;
     }
@@ -827,6 +861,7 @@ static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
     StageAcc ha;
     CK(cudaMemcpyAsync(&ha, e->d_acc, sizeof ha, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    if (ha.n_desc) { const int rc = check_sorted_host(e, n); if (rc) return rc; }
     e->acc_n_kept = (int64_t)ha.n_kept; e->max_rend = ha.n_kept ? ha.max_rend : 0;
     e->sum_rlen = ha.sum_rlen; e->sum_indel_text = ha.sum_indel_text;
     // ---- column domain
@@ -873,6 +908,8 @@ static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
     CK(cudaStreamSynchronize(e->stream));
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_stage_ms = ms;
     cudaEventElapsedTime(&ms, e->evA, e->ev1); e->last_stage_device_ms = ms;
+    e->last_baq_ms = 0;
+    if (e->baq_ran) { cudaEventElapsedTime(&ms, e->evB0, e->evB1); e->last_baq_ms = ms; }
     e->staged = true;
     if (stats) {
         stats->n_kept = (int64_t)ha.n_kept; stats->n_kept_in_window = (int64_t)ha.n_kept_in_window;
@@ -901,6 +938,7 @@ extern "C" int b200_restage(b200_engine_t *e, b200_stage_stats_t *stats)
     return stage_device(e, stats);
 }
 extern "C" double b200_last_stage_device_ms(const b200_engine_t *e) { return e ? e->last_stage_device_ms : 0; }
+extern "C" double b200_last_baq_ms(const b200_engine_t *e) { return e ? e->last_baq_ms : 0; }
 
 int build_ranges(b200_engine *e, int *max_range)
 {
@@ -1170,26 +1208,28 @@ extern "C" int b200_pileup_entries(b200_engine_t *e, int32_t file, int64_t beg, 
     if (re > v.ncols) re = v.ncols;
     *n_entries = 0;
     if (re <= rb) return 0;
+    // only the slab [rb,re): counts, their scan and the entries are sized by the slab, not by the contig
     v.ncols = (int32_t)re;
-    ENSURE(col_n, (size_t)re + 1); ENSURE(col_off, (size_t)re + 2);
-    k_entries_count<<<nblk(re, 256), 256, 0, e->stream>>>(v, file, e->col_n); e->launches++;
-    const int nb = nblk(re, 256);
+    const int64_t nc = re - rb;
+    ENSURE(col_n, (size_t)nc + 1); ENSURE(col_off, (size_t)nc + 2);
+    k_entries_count<<<nblk(nc, 256), 256, 0, e->stream>>>(v, file, (int32_t)rb, e->col_n); e->launches++;
+    const int nb = nblk(nc, 256);
     ENSURE(status, (size_t)nb + 1);
     CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
     CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
-    k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->col_n, e->col_off, (int32_t)re, e->status, (uint32_t *)e->d_misc); e->launches++;
-    uint64_t tot = 0, first = 0;
-    CK(cudaMemcpyAsync(&tot, e->col_off + re, 8, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaMemcpyAsync(&first, e->col_off + rb, 8, cudaMemcpyDeviceToHost, e->stream));
+    k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->col_n, e->col_off, (int32_t)nc, e->status, (uint32_t *)e->d_misc); e->launches++;
+    uint64_t tot = 0;
+    CK(cudaMemcpyAsync(&tot, e->col_off + nc, 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    ENSURE(ents, (size_t)tot + 1);
-    k_entries_fill<<<nblk(re, 256), 256, 0, e->stream>>>(v, file, e->col_off, e->ents, e->h_file_start[file]); e->launches++;
     CK(cudaGetLastError());
-    const size_t ne = (size_t)(tot - first);
+    const size_t ne = (size_t)tot;
     *n_entries = ne;
-    if (ne > cap_entries) { snprintf(e->err, sizeof e->err, "entry buffer too small: need %zu", ne); return -2; }
-    CK(cudaMemcpyAsync(col_n, e->col_n + rb, (size_t)(re - rb) * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (ne) CK(cudaMemcpyAsync(entries, e->ents + first, ne * sizeof(b200_pileup1_t), cudaMemcpyDeviceToHost, e->stream));
+    if (ne > cap_entries) { snprintf(e->err, sizeof e->err, "entry buffer too small: need %zu", ne); return -2; }   // before any fill work
+    ENSURE(ents, ne + 1);
+    k_entries_fill<<<nblk(nc, 256), 256, 0, e->stream>>>(v, file, (int32_t)rb, e->col_off, e->ents); e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(col_n, e->col_n, (size_t)nc * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (ne) CK(cudaMemcpyAsync(entries, e->ents, ne * sizeof(b200_pileup1_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return 0;
 }

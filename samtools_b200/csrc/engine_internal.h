@@ -12,7 +12,8 @@
 struct b200_engine {
     int device = 0, n_sm = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr, evB0 = nullptr, evB1 = nullptr;
+    bool baq_ran = false; double last_baq_ms = 0;
     double last_parts_ms[3] = {0, 0, 0};
     char err[512];
     int64_t launches = 0;

@@ -230,6 +230,17 @@ extern "C" int b200_glf(b200_engine_t *e, int32_t min_baseQ, int64_t *n_cols, in
     CK(cudaEventRecord(e->ev1, e->stream));
     uint64_t total_draws = 0;
     CK(cudaMemcpyAsync(&total_draws, e->col_off + tot, 8, cudaMemcpyDeviceToHost, e->stream));
+    if (!col_pos) {   // device-only: the likelihoods stay in HBM
+        uint32_t h_ovf = 0;
+        CK(cudaMemcpyAsync(&h_ovf, ovf, 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaGetLastError());
+        float ms0 = 0; cudaEventElapsedTime(&ms0, e->ev0, e->ev1); e->last_kernel_ms = ms0;
+        e->gl_rng_draws += total_draws;
+        if (h_ovf) { snprintf(e->err, sizeof e->err, "GL: a column holds more than %d usable bases", GL_CAP); return -1; }
+        *n_cols = v.ncols;
+        return 0;
+    }
     std::vector<uint32_t> flag((size_t)v.ncols + 1);
     std::vector<int32_t> hn((size_t)tot);
     std::vector<float> ho((size_t)tot * 29);

@@ -45,8 +45,15 @@ bool load_file(const std::string &fn, const std::string &fai, const char *reg, F
     }
     fd.by_tid.resize((size_t)fd.rd->header().n_ref());
     Record r; int ret;
+    int last_tid = -1;
     while ((ret = fd.rd->next(r)) >= 0) {
         if (r.tid < 0 || r.tid >= (int)fd.by_tid.size()) { ++fd.n_no_tid; continue; }
+        if (!(r.flag & F_UNMAP)) {
+            // records are bucketed per reference sequence below, which would silently repair a file whose chromosomes are
+            // out of order; htslib's bam_plp_push refuses it (order within a sequence is checked by the engine's read stage)
+            if (r.tid < last_tid) { fprintf(stderr, "[%s] The input is not sorted (chromosomes out of order)\n", cmd); return false; }
+            last_tid = r.tid;
+        }
         fd.by_tid[(size_t)r.tid].push_back(std::move(r));
     }
     if (ret < -1) { fprintf(stderr, "samtools %s: error reading from input file\n", cmd); return false; }

@@ -248,7 +248,7 @@ int AlnReader::parse_sam(char *line, Record &r)
         while (*c) {
             char *e; unsigned long l = strtoul(c, &e, 10);
             const char *o = *e ? strchr(kOps, *e) : nullptr;
-            if (!o) return -2;
+            if (!o || o - kOps > 8) return -2;                            // 'B' (and anything else) is not an alignment op
             r.cigar.push_back((uint32_t)l << 4 | (uint32_t)(o - kOps));
             c = e + 1;
         }
@@ -314,12 +314,31 @@ int AlnReader::read_bam(Record &r)
     memcpy(&r.mtid, &d[20], 4);
     memcpy(&i32, &d[24], 4); r.mpos = i32;
     memcpy(&i32, &d[28], 4); r.isize = i32;
+    // the variable part must fit the block (a truncated / corrupt record must not be read past its end)
+    if (r.l_qseq < 0 || l_name < 1 ||
+        32ull + (uint64_t)l_name + 4ull * ncig + ((uint64_t)r.l_qseq + 1) / 2 + (uint64_t)r.l_qseq > (uint64_t)bs) return -2;
     const uint8_t *p = d.data() + 32;
     r.qname.assign((const char *)p, strnlen((const char *)p, (size_t)l_name)); p += l_name;
     r.cigar.resize(ncig); if (ncig) memcpy(r.cigar.data(), p, 4 * (size_t)ncig); p += 4 * (size_t)ncig;
     r.seq4.assign(p, p + (r.l_qseq + 1) / 2); p += (r.l_qseq + 1) / 2;
     r.qual.assign(p, p + r.l_qseq); p += r.l_qseq;
     r.aux.assign(p, (const uint8_t *)d.data() + bs);
+    for (uint32_t c : r.cigar) if ((c & 0xf) > 8) return -2;          // only MIDNSHP=X are defined for alignments
+    // long CIGARs (> 65535 ops) live in the CG:B,I tag behind a <l_qseq>S<rlen>N placeholder (SAMv1 4.2.2; htslib bam_tag2cigar)
+    if (r.cigar.size() == 2 && (r.cigar[0] & 0xf) == 4 && (int32_t)(r.cigar[0] >> 4) == r.l_qseq && (r.cigar[1] & 0xf) == 3) {
+        const uint8_t *cg = r.aux_get("CG");
+        if (cg && cg[0] == 'B' && cg[1] == 'I') {
+            uint32_t n; memcpy(&n, cg + 2, 4);
+            const size_t off = (size_t)(cg - r.aux.data());
+            if (n > 0 && off + 6 + 4ull * n <= r.aux.size()) {
+                std::vector<uint32_t> real(n);
+                memcpy(real.data(), cg + 6, 4ull * n);
+                for (uint32_t c : real) if ((c & 0xf) > 8) return -2;
+                r.cigar.swap(real);
+                r.aux.erase(r.aux.begin() + (long)off - 2, r.aux.begin() + (long)(off + 6 + 4ull * n));   // drop the tag like htslib does
+            }
+        }
+    }
     return 0;
 }
 

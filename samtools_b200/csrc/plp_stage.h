@@ -35,6 +35,7 @@ struct RawSoA {
 
 struct StageAcc {   // device-side accumulators (one instance per stage call)
     unsigned long long n_kept, n_kept_in_window, sum_rlen, sum_indel_text, n_reads, n_selected, summed_mapq;
+    unsigned long long n_desc;   // records whose start lies before the previous record's (any file, any state): triggers the exact sortedness check
     int max_rend;
 };
 
@@ -202,6 +203,7 @@ PLP_HD void stage_build_desc(const RawSoA &r, const b200_stage_conf_t &cf, int64
         }
     }
     desc[i] = d;
+    if (i > 0 && r.pos[i] < r.pos[i - 1]) PLP_ADD64(&acc->n_desc, 1);   // bam_plp_push rejects unsorted input; see check_sorted_host()
     // end used for the running max that bounds the per-group read slices: capped at rpos + kReach, because from
     // there on the read is served through the far-reaching lists (k_ovf_*) and must not widen the slices under it
     endv[i] = d.rend > d.rpos ? (d.rend - d.rpos > kReach ? d.rpos + kReach : d.rend) : INT32_MIN;

@@ -19,7 +19,7 @@ POS_MAX = (0x7fffffff << 32) | 0xffffffff
 EXPORTS = ['b200_engine_create', 'b200_engine_destroy', 'b200_last_error', 'b200_version', 'b200_stage',
            'b200_mpileup_text', 'b200_depth_text', 'b200_coverage', 'b200_glf', 'b200_fetch_qual',
            'b200_fetch_mapq_keep', 'b200_pileup_entries', 'b200_last_kernel_ms', 'b200_last_stage_ms', 'b200_set_keep_raw', 'b200_restage', 'b200_last_stage_device_ms',
-           'b200_launch_count', 'b200_last_mpileup_parts_ms']
+           'b200_launch_count', 'b200_last_mpileup_parts_ms', 'b200_gl_rng_draws', 'b200_last_baq_ms']
 
 
 class Batch(C.Structure):
@@ -97,6 +97,8 @@ def load_library():
         lib.b200_restage.argtypes = [C.c_void_p, C.c_void_p]; lib.b200_restage.restype = C.c_int
         lib.b200_launch_count.argtypes = [C.c_void_p]; lib.b200_launch_count.restype = C.c_int64
         lib.b200_last_mpileup_parts_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double * 3)]
+        lib.b200_last_baq_ms.argtypes = [C.c_void_p]; lib.b200_last_baq_ms.restype = C.c_double
+        lib.b200_gl_rng_draws.argtypes = [C.c_void_p]; lib.b200_gl_rng_draws.restype = C.c_uint64
         _lib = lib
     return _lib
 
@@ -212,8 +214,12 @@ class Engine:
             self._err('b200_coverage')
         return {k: getattr(s, k) for k, _ in CoverageSums._fields_}
 
-    def glf(self, min_baseQ, cap_cols, n_files=1):
+    def glf(self, min_baseQ, cap_cols, n_files=1, fetch=True):
         n = C.c_int64(0)
+        if not fetch:     # compute only; the likelihoods stay in HBM
+            if self.lib.b200_glf(self.h, min_baseQ, C.byref(n), None, None, None, None, 0) != 0:
+                self._err('b200_glf')
+            return n.value
         pos = np.zeros(cap_cols, np.int64); nb = np.zeros(cap_cols * n_files, np.int32)
         qs = np.zeros(cap_cols * n_files * 4, np.float32); p25 = np.zeros(cap_cols * n_files * 25, np.float32)
         if self.lib.b200_glf(self.h, min_baseQ, C.byref(n), _ptr(pos), _ptr(nb), _ptr(qs), _ptr(p25), cap_cols) != 0:
@@ -249,10 +255,19 @@ class Engine:
         return self.lib.b200_last_stage_device_ms(self.h)
 
     @property
+    def last_baq_ms(self):
+        return self.lib.b200_last_baq_ms(self.h)
+
+    @property
     def last_mpileup_parts_ms(self):
         a = (C.c_double * 3)()
         self.lib.b200_last_mpileup_parts_ms(self.h, C.byref(a))
         return list(a)
+
+    @property
+    def gl_rng_draws(self):
+        """hts_drand48 draws consumed so far by errmod_cal's ks_shuffle (columns with more than 255 usable bases)"""
+        return self.lib.b200_gl_rng_draws(self.h)
 
     @property
     def launches(self):

@@ -70,3 +70,14 @@ def gather_payload(local, sizes, dst=0):
                 dist.recv(out[off:off + n], src=r)
         off += n
     return out
+
+
+def select_window(soa, beg, end):
+    """The reads a region shard [beg,end) stages: every read with pos < end and end position > beg (the `-r` rule,
+    bam_plcmd.c:550-554 / htslib's region iterator; zero-span reads count as one base), re-packed as their own batch."""
+    import numpy as np
+    from . import synth
+    pos = soa['pos']
+    rl = np.maximum(synth.ref_span(soa), 1)
+    idx = np.nonzero((pos < end) & (pos + rl > beg))[0]
+    return synth.take_reads(soa, idx)

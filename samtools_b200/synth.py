@@ -45,15 +45,20 @@ def _name_odd(pair_id, width=9):
 
 def make_batch(length=1_000_000, depth=30, read_len=150, seed=2, ref=None, ref_seed=1, with_ref=True, tid=0,
                tid_name='chr1', frac_ins=0.015, frac_del=0.015, frac_clip=0.02, frac_skip=0.001, frac_flag=0.005,
-               paired=True):
-    """Returns a dict with the b200_batch_t arrays (+ 'pair_id', 'ref' ...)."""
+               paired=True, n_pairs=None, start_lo=0, start_span=None):
+    """Returns a dict with the b200_batch_t arrays (+ 'pair_id', 'ref' ...).
+    n_pairs / start_lo / start_span override the uniform whole-contig placement (used by make_panel: the
+    leftmost mates start inside [start_lo, start_lo + start_span))."""
     rng = np.random.default_rng(seed)
     L = read_len
     if ref is None:
         ref = make_reference(length, ref_seed)
-    n_pairs = int(round(depth * length / (2.0 * L)))
+    if n_pairs is None:
+        n_pairs = int(round(depth * length / (2.0 * L)))
     isize = np.clip(rng.normal(400, 50, n_pairs).round().astype(np.int64), L, 1000)
-    start = rng.integers(0, max(1, length - 3200), size=n_pairs).astype(np.int64)   # reads (even with a 2 kb N skip) stay inside the contig
+    if start_span is None:
+        start_span = max(1, length - 3200 - start_lo)                               # reads (even with a 2 kb N skip) stay inside the contig
+    start = (start_lo + rng.integers(0, max(1, start_span), size=n_pairs)).astype(np.int64)
     # which mate is first / forward
     fwd_first = rng.random(n_pairs) < 0.5
     n = 2 * n_pairs
@@ -219,3 +224,155 @@ def write_sam(path, soa, max_reads=None):
             paired = bool(soa['flag'][i] & 1)
             f.write(f'p{int(soa["pair_id"][i]):09d}\t{int(soa["flag"][i])}\t{name}\t{int(soa["pos"][i]) + 1}\t{int(soa["mapq"][i])}\t{cg}\t'
                     f'{"=" if paired else "*"}\t{int(soa["mpos"][i]) + 1}\t{int(soa["isize"][i])}\t{seq}\t{ql}\n')
+
+
+def ref_span(soa):
+    """bam_cigar2rlen per read (reference bases consumed: M, D, N, =, X)."""
+    cg = soa['cigar']
+    op = cg & 0xf
+    ln = np.where((op == 0) | (op == 2) | (op == 3) | (op == 7) | (op == 8), cg >> 4, 0).astype(np.int64)
+    cs = np.concatenate([[0], np.cumsum(ln)])
+    o = soa['cigar_off'].astype(np.int64)
+    return cs[o + soa['n_cigar'].astype(np.int64)] - cs[o]
+
+
+def _gather_ranges(off, cnt):
+    """indices off[i] .. off[i]+cnt[i]-1 for every i, concatenated."""
+    cnt = cnt.astype(np.int64)
+    tot = int(cnt.sum())
+    if tot == 0:
+        return np.zeros(0, dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    return np.repeat(off.astype(np.int64) - starts, cnt) + np.arange(tot, dtype=np.int64)
+
+
+def take_reads(soa, idx):
+    """Sub-batch holding reads `idx` (ascending batch indices, or a permutation), payload re-packed; name links that
+    leave the selection become -1.  All reads must have the same l_qseq (true of this generator)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    n0 = len(soa['pos'])
+    L = soa['read_len']; lq = L + (L & 1)
+    out = dict(soa)
+    for k in ('pos', 'flag', 'mapq', 'l_qseq', 'n_cigar', 'mtid', 'mpos', 'isize', 'rbits', 'pair_id'):
+        out[k] = np.ascontiguousarray(soa[k][idx])
+    inv = np.full(n0 + 1, -1, dtype=np.int64)
+    inv[idx] = np.arange(len(idx), dtype=np.int64)
+    prev = soa['prev_same_name'][idx]
+    out['prev_same_name'] = np.where(prev >= 0, inv[np.where(prev >= 0, prev, n0)], -1).astype(np.int64)
+    rows = (soa['qual_off'][idx] // np.uint64(lq)).astype(np.int64)
+    out['qual'] = np.ascontiguousarray(soa['qual'].reshape(-1, lq)[rows].reshape(-1))
+    out['seq4'] = np.ascontiguousarray(soa['seq4'].reshape(-1, lq // 2)[rows].reshape(-1))
+    out['qual_off'] = np.arange(len(idx), dtype=np.uint64) * np.uint64(lq)
+    out['cigar'] = np.ascontiguousarray(soa['cigar'][_gather_ranges(soa['cigar_off'][idx], out['n_cigar'])])
+    out['cigar_off'] = np.concatenate([[0], np.cumsum(out['n_cigar'].astype(np.int64))[:-1]]).astype(np.uint64)
+    out['file_start'] = np.array([0, len(idx)], dtype=np.int64)
+    return out
+
+
+def make_panel(n_targets=500, target_len=2000, depth=200, n_hot=20, hot_depth=2000, hot_span=100, spacing=10_000,
+               read_len=150, seed=4, with_ref=True, tid_name='chr1', **kw):
+    """BASELINE config 4 shape: `n_targets` targets of `target_len` bp at `depth`x mean, `n_hot` of them
+    carrying a hotspot where another `hot_depth`x of pairs start inside `hot_span` bp (columns with thousands of reads,
+    i.e. errmod_cal's n > 255 shuffle path).  One contig, targets `spacing` bp apart; coordinate sorted."""
+    L = read_len
+    length = n_targets * spacing
+    rng = np.random.default_rng(seed)
+    hot = set(rng.choice(n_targets, size=min(n_hot, n_targets), replace=False).tolist()) if n_hot else set()
+    ref = make_reference(length, seed * 1000 + 1)
+    parts = []
+    npair = 0
+    for t in range(n_targets):
+        off = t * spacing
+        sub = ref[off:off + spacing]
+        pieces = [dict(n_pairs=int(round(depth * target_len / (2.0 * L))), start_lo=200, start_span=target_len, seed=seed * 100003 + 2 * t)]
+        if t in hot:
+            pieces.append(dict(n_pairs=int(round(hot_depth * (hot_span + L) / (2.0 * L))), start_lo=200 + target_len // 2, start_span=hot_span,
+                               seed=seed * 100003 + 2 * t + 1))
+        for pc in pieces:
+            b = make_batch(length=spacing, read_len=L, ref=sub, with_ref=True, tid_name=tid_name, **pc, **kw)
+            parts.append((off, b, npair))
+            npair += int(b['pair_id'].max()) + 1 if len(b['pair_id']) else 0
+    nread = np.cumsum([0] + [len(p['pos']) for _, p, _ in parts])
+    ncig = np.cumsum([0] + [len(p['cigar']) for _, p, _ in parts])
+    nq = np.cumsum([0] + [len(p['qual']) for _, p, _ in parts])
+    out = {}
+    out['pos'] = np.concatenate([p['pos'] + o for o, p, _ in parts]); out['mpos'] = np.concatenate([p['mpos'] + o for o, p, _ in parts])
+    for k_ in ('flag', 'mapq', 'l_qseq', 'n_cigar', 'mtid', 'isize', 'cigar', 'seq4', 'qual'):
+        out[k_] = np.concatenate([p[k_] for _, p, _ in parts])
+    out['cigar_off'] = np.concatenate([p['cigar_off'] + np.uint64(ncig[i]) for i, (_, p, _) in enumerate(parts)])
+    out['qual_off'] = np.concatenate([p['qual_off'] + np.uint64(nq[i]) for i, (_, p, _) in enumerate(parts)])
+    out['prev_same_name'] = np.concatenate([np.where(p['prev_same_name'] >= 0, p['prev_same_name'] + nread[i], -1) for i, (_, p, _) in enumerate(parts)])
+    out['pair_id'] = np.concatenate([p['pair_id'] + base for _, p, base in parts])
+    out['rbits'] = (_name_odd(out['pair_id']) * 2).astype(np.uint8)
+    out['file_start'] = np.array([0, nread[-1]], dtype=np.int64)
+    out.update(tid=0, tid_len=length, tid_name=tid_name, ref=ref if with_ref else None, ref_beg=0, ref_len=length, read_len=L, ref_full=ref)
+    order = np.argsort(out['pos'], kind='stable')              # hotspot pieces interleave with their target's reads
+    res = take_reads(out, order)
+    res['hot_targets'] = sorted(hot)
+    return res
+
+
+def _reg2bin(beg, end):
+    """SAMv1 5.3 reg2bin, vectorised (end exclusive)."""
+    end = end - 1
+    b = np.zeros(len(beg), dtype=np.int64)
+    done = np.zeros(len(beg), dtype=bool)
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        m = ~done & ((beg >> shift) == (end >> shift))
+        b[m] = base + (beg[m] >> shift)
+        done |= m
+    return b.astype(np.uint16)
+
+
+def write_bam(path, soa, level=1, block=0xff00):
+    """The same records as a coordinate-sorted BAM (BGZF, SAMv1 4.2): what `samtools mpileup` really reads.
+    Names are p%09d like write_sam().  No index is written (the readers here scan)."""
+    import struct
+    import zlib
+    name = soa['tid_name'].encode(); L = soa['read_len']; lq = L + (L & 1)
+    n = len(soa['pos'])
+    text = f'@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:{soa["tid_name"]}\tLN:{soa["tid_len"]}\n'.encode()
+    hdr = b'BAM\1' + struct.pack('<i', len(text)) + text + struct.pack('<i', 1) + struct.pack('<i', len(name) + 1) + name + b'\0' + \
+        struct.pack('<i', int(soa['tid_len']))
+    ncg = soa['n_cigar'].astype(np.int64)
+    fixed = 32 + 11 + (L + 1) // 2 + L
+    size = fixed + 4 * ncg                                   # block_size field excluded
+    off = np.concatenate([[0], np.cumsum(size + 4)])
+    buf = np.zeros(int(off[-1]), dtype=np.uint8)
+    rl = ref_span(soa)
+    pos = soa['pos'].astype(np.int64)
+    core = np.zeros(n, dtype=np.dtype([('bs', '<i4'), ('tid', '<i4'), ('pos', '<i4'), ('lname', 'u1'), ('mapq', 'u1'), ('bin', '<u2'), ('ncig', '<u2'),
+                                        ('flag', '<u2'), ('lseq', '<i4'), ('mtid', '<i4'), ('mpos', '<i4'), ('tlen', '<i4')]))
+    core['bs'] = size; core['tid'] = soa.get('tid', 0); core['pos'] = pos; core['lname'] = 11; core['mapq'] = soa['mapq']
+    core['bin'] = _reg2bin(pos, pos + np.maximum(rl, 1)); core['ncig'] = ncg; core['flag'] = soa['flag']; core['lseq'] = L
+    core['mtid'] = soa['mtid']; core['mpos'] = soa['mpos']; core['tlen'] = soa['isize']
+    cb = core.view(np.uint8).reshape(n, 36)
+    digits = np.zeros((n, 11), dtype=np.uint8); digits[:, 0] = ord('p')
+    pid = soa['pair_id'].astype(np.int64)
+    for k in range(9):
+        digits[:, 9 - k] = ord('0') + (pid // 10 ** k) % 10
+    rows = (soa['qual_off'] // np.uint64(lq)).astype(np.int64)
+    seq = soa['seq4'].reshape(-1, lq // 2)[rows][:, :(L + 1) // 2].copy()
+    if L & 1:
+        seq[:, -1] &= 0xf0
+    qual = soa['qual'].reshape(-1, lq)[rows][:, :L]
+    o = off[:-1]
+    for cols, at in ((cb, 0), (digits, 36)):
+        buf[(o[:, None] + at + np.arange(cols.shape[1])[None, :]).reshape(-1)] = cols.reshape(-1)
+    cig_bytes = soa['cigar'].astype('<u4').view(np.uint8)
+    dst = np.repeat(o + 47, 4 * ncg) + (np.arange(int(4 * ncg.sum())) - np.repeat(np.concatenate([[0], np.cumsum(4 * ncg)[:-1]]), 4 * ncg))
+    src = _gather_ranges(4 * soa['cigar_off'].astype(np.int64), 4 * ncg)
+    buf[dst] = cig_bytes[src]
+    so = o + 47 + 4 * ncg
+    buf[(so[:, None] + np.arange(seq.shape[1])[None, :]).reshape(-1)] = seq.reshape(-1)
+    qo = so + seq.shape[1]
+    buf[(qo[:, None] + np.arange(L)[None, :]).reshape(-1)] = qual.reshape(-1)
+    data = hdr + buf.tobytes()
+    with open(path, 'wb') as f:
+        for i in range(0, len(data), block):
+            chunk = data[i:i + block]
+            c = zlib.compressobj(level, zlib.DEFLATED, -15)
+            comp = c.compress(chunk) + c.flush()
+            f.write(b'\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0' + struct.pack('<H', len(comp) + 25) + comp +
+                    struct.pack('<II', zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+        f.write(bytes.fromhex('1f8b08040000000000ff0600424302001b0003000000000000000000'))

@@ -39,6 +39,8 @@ const char *b200_last_error(const b200_engine_t *e) { return e->err.c_str(); }
 double b200_last_kernel_ms(const b200_engine_t *) { return 0; }
 double b200_last_stage_ms(const b200_engine_t *) { return 0; }
 int64_t b200_launch_count(const b200_engine_t *) { return 0; }
+uint64_t b200_gl_rng_draws(const b200_engine_t *) { return 0; }
+double b200_last_baq_ms(const b200_engine_t *) { return 0; }
 void b200_last_mpileup_parts_ms(const b200_engine_t *, double *ms3) { ms3[0] = ms3[1] = ms3[2] = 0; }
 int b200_engine_create(int, b200_engine_t **out) { *out = new b200_engine(); return 0; }
 void b200_engine_destroy(b200_engine_t *e) { delete e; }
@@ -123,6 +125,15 @@ int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t 
     }
     for (int64_t i = 0; i < n; ++i) stage_prep2(r, *cf, i, e->state.data());
     for (int64_t i = 0; i < n; ++i) stage_build_desc(r, *cf, i, e->state.data(), e->rlen.data(), e->desc.data(), e->endv.data(), &e->acc, e->win_base, e->cig_x.data(), e->cig_y.data());
+    if (e->acc.n_desc)   // same rule as check_sorted_host() in engine.cu
+        for (int f = 0; f < b->n_files; ++f) {
+            bool have = false; int32_t last = 0;
+            for (int64_t i = b->file_start[f]; i < b->file_start[f + 1]; ++i) {
+                if (e->state[(size_t)i] != ST_KEEP) continue;
+                if (have && e->desc[(size_t)i].rpos < last) { e->err = cf->mode == B200_MODE_DEPTH ? "Data is not position sorted" : "The input is not sorted (reads out of order)"; return -3; }
+                have = true; last = e->desc[(size_t)i].rpos;
+            }
+        }
     const int32_t max_rend = e->acc.n_kept ? e->acc.max_rend : 0;
     int64_t wend = cf->end - e->win_base, cov = max_rend > 0 ? max_rend : 0;
     if (cov > wend) cov = wend;

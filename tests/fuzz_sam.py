@@ -101,3 +101,5 @@ MPILEUP_OPTS = [
 DEPTH_OPTS = ['', '-a', '-aa', '-J', '-q 13', '-Q 20 -l 10', '-s', '-s -J -q 14', '-g 0x400', '-G 16', '--incl-flags 0x40', '--require-flags 0x3',
               '-r c0:50-400', '-a -r c1:1-100', '-b {bed}', '-aa -b {bed}', '-H']
 COVERAGE_OPTS = ['', '-q 20', '-Q 13', '--min-depth 2', '-l 20', '--ff 0', '--rf 0x10', '-r c0:50-400', '-r c1', '-H']
+# genotype likelihoods (bcf_call_glfgen + errmod_cal per column and file); CUDA path only: the emulation harness has no GL
+GL_OPTS = ['-B', '-B -Q 0', '-B -x -A', '-B -q 20', '-B -r c0:50-400', '-B -6 -Q 0', '']

@@ -12,7 +12,7 @@ def emul_bin():
     return os.path.join(ROOT, 'tests', 'emul', '_build', 'b200samtools_emul')
 
 
-def run_all(tool, oracle, td, seeds, need_noBAQ):
+def run_all(tool, oracle, td, seeds, need_noBAQ, with_gl=False):
     """every (seed, command line): oracle output vs tool output; a few processes in flight (the cases are independent
     and read-only; on the GPU each tool process pays ~1 s of CUDA context creation)"""
     from concurrent.futures import ThreadPoolExecutor
@@ -26,14 +26,16 @@ def run_all(tool, oracle, td, seeds, need_noBAQ):
         (d / 'x2.sam').write_text(fuzz_sam.make_sam(seed + 100000, n_reads=25)[0])
         cases = [('mpileup', o) for o in fuzz_sam.MPILEUP_OPTS] + [('depth', o) for o in fuzz_sam.DEPTH_OPTS] + \
                 [('coverage', o) for o in fuzz_sam.COVERAGE_OPTS]
+        if with_gl:
+            cases += [('gl', o) for o in fuzz_sam.GL_OPTS]
         for cmd, opt in cases:
-            if need_noBAQ and cmd == 'mpileup' and '-B' not in opt.split():
+            if need_noBAQ and cmd in ('mpileup', 'gl') and '-B' not in opt.split():
                 continue
             if seed % 5 == 0 and ((cmd == 'depth' and ('-q' in opt.split() or '-J' in opt.split())) or (cmd == 'mpileup' and '-C' in opt.split())):
                 continue   # undefined upstream on SEQ '*' records
             opt = opt.format(bed='x.bed', rg='rg.txt')
             files = 'x.sam x2.sam' if (seed % 3 == 0 and '-r' not in opt) else 'x.sam'
-            ref = '-f x.fa' if cmd == 'mpileup' and seed % 4 != 1 else ''
+            ref = '-f x.fa' if cmd in ('mpileup', 'gl') and seed % 4 != 1 else ''
             tasks.append((seed, f'{cmd} {opt} {ref} {files}', d))
 
     def one(t):

@@ -8,8 +8,8 @@ pytestmark = pytest.mark.gpu
 CLI = os.path.join(ROOT, 'samtools_b200', 'bin', 'b200samtools')
 
 
-@pytest.mark.parametrize('lo', [1])
+@pytest.mark.parametrize('lo', [1, 5])
 def test_fuzz_cuda_path(lo, oracle_bin, tmp_path):
-    # two seeds (~140 CLI runs, each paying a CUDA context): 12 seeds were run clean during development
-    bad = run_all(CLI, oracle_bin, tmp_path, range(lo, lo + 2), need_noBAQ=False)
+    # 2 x 4 seeds (~500 CLI runs, each paying a CUDA context, 6 in flight), GL included
+    bad = run_all(CLI, oracle_bin, tmp_path, range(lo, lo + 4), need_noBAQ=False, with_gl=True)
     assert not bad, f'{len(bad)} mismatches, first: {bad[0]}'

@@ -202,6 +202,130 @@ def test_c2_size_properties():
     assert len(set(digests.values())) == 1, digests   # read-major / column-major / chained single-launch kernels, TMA / vector / direct-to-HBM stores all agree
 
 
+# ---------------------------------------------------------------- BASELINE C2 size, CUDA bytes vs the oracle's bytes
+@pytest.fixture(scope='module')
+def c2_set(tmp_path_factory, oracle_bin):
+    """BASELINE config 2: 1 Mb, 30x, 150 bp (200 000 reads).  The oracle needs ~1 s (-a), ~8 s (-f, BAQ) for it."""
+    from samtools_b200 import synth
+    td = tmp_path_factory.mktemp('c2')
+    soa = synth.make_batch(length=1_000_000, depth=30, seed=2)
+    sam, fa = str(td / 'c2.sam'), str(td / 'c2.fa')
+    synth.write_sam(sam, soa); synth.write_fasta(fa, soa['tid_name'], soa['ref_full'])
+    return dict(soa=soa, sam=sam, fa=fa, oracle=oracle_bin)
+
+
+def _same(got, want, what):
+    if got != want:
+        n = min(len(got), len(want))
+        a = np.frombuffer(got[:n], np.uint8); b = np.frombuffer(want[:n], np.uint8)
+        d = int(np.argmax(a != b)) if (a != b).any() else n
+        lo = max(0, d - 120)
+        raise AssertionError(f'{what}: first difference at byte {d} of {len(want)} (got {len(got)})\n got: {got[lo:d + 80]!r}\nwant: {want[lo:d + 80]!r}')
+
+
+def test_c2_mpileup_a_vs_oracle(c2_set, eng):
+    from samtools_b200 import engine
+    eng.stage(noref(c2_set['soa']), engine.default_stage_conf(engine.MODE_MPILEUP))
+    _same(eng.mpileup_text(all=1), oracle_out(c2_set, 'mpileup', '-a', c2_set['sam']), 'mpileup -a (C2, no FASTA)')
+
+
+def test_c2_mpileup_f_baq_vs_oracle(c2_set, eng):
+    """the default mode of `mpileup -f`: BAQ (sam_prob_realn on every read) + mate-overlap tweak, 200 000 reads"""
+    from samtools_b200 import engine
+    eng.stage(c2_set['soa'], engine.default_stage_conf(engine.MODE_MPILEUP))
+    _same(eng.mpileup_text(), oracle_out(c2_set, 'mpileup', '-f', c2_set['fa'], c2_set['sam']), 'mpileup -f (C2, BAQ + overlap)')
+    _same(eng.mpileup_text(all=1, out_mapq=1), oracle_out(c2_set, 'mpileup', '-a', '-s', '-f', c2_set['fa'], c2_set['sam']), 'mpileup -a -s -f (C2)')
+
+
+def test_c2_depth_coverage_vs_oracle(c2_set, eng):
+    from samtools_b200 import engine
+    soa = c2_set['soa']
+    eng.stage(soa, engine.default_stage_conf(engine.MODE_DEPTH))
+    _same(eng.depth_text(all=1), oracle_out(c2_set, 'depth', '-a', c2_set['sam']), 'depth -a (C2)')
+    st = eng.stage(soa, engine.default_stage_conf(engine.MODE_COVERAGE, rflag_filter=4 | 256 | 512 | 1024, end=soa['tid_len']))
+    s = eng.coverage(min_baseQ=0, min_depth=1)
+    row = oracle_out(c2_set, 'coverage', c2_set['sam']).split(b'\n')[1].split(b'\t')
+    L = float(soa['tid_len'])
+    fmt = lambda x, f: (f % x).encode()
+    assert int(row[3]) == st.n_selected_reads and int(row[4]) == s['n_covered_bases']
+    assert row[5] == fmt(100.0 * s['n_covered_bases'] / L, '%g') and row[6] == fmt(s['summed_coverage'] / L, '%g')
+    assert row[7] == fmt(s['summed_baseQ'] / s['quality_bases'], '%.3g') and row[8] == fmt(st.summed_mapq / st.n_selected_reads, '%.3g')
+
+
+# ---------------------------------------------------------------- BASELINE C4 shape: deep columns -> GL (errmod_cal n > 255)
+def test_c4_panel_gl_every_column(tmp_path, oracle_bin, eng):
+    """200x targets with 2000x hotspots: every column's n, qsum[4] and p[25] against the oracle, including the columns with
+    more than 255 usable bases (ks_shuffle over the hts_drand48 stream, LCG jump-ahead on the device) and the number of
+    random draws consumed (the stream position a following call would continue from)."""
+    from samtools_b200 import engine, synth
+    soa = synth.make_panel(n_targets=12, n_hot=3, seed=4)
+    sam, fa = str(tmp_path / 'c4.sam'), str(tmp_path / 'c4.fa')
+    synth.write_sam(sam, soa); synth.write_fasta(fa, soa['tid_name'], soa['ref_full'])
+    st = eng.stage(soa, engine.default_stage_conf(engine.MODE_MPILEUP, baq=0))
+    d0 = eng.gl_rng_draws
+    pos, n, qs, p25 = eng.glf(13, int(st.n_cols) + 16)
+    lines = subprocess.run([oracle_bin, 'gl', '-B', '-f', fa, sam], capture_output=True, check=True).stdout.decode().split('\n')[:-1]
+    assert len(lines) == len(pos)
+    want = np.array([[np.float32(x) for x in l.split('\t')[3:33]] for l in lines], dtype=np.float32)
+    wpos = np.array([int(l.split('\t', 2)[1]) for l in lines])
+    assert (wpos == pos + 1).all()
+    wn = want[:, 0].astype(np.int64)
+    assert (wn > 255).sum() > 500 and wn.max() > 1500, 'the panel must exercise the shuffle path'
+    assert (np.maximum(n[:, 0], 0) == wn).all()
+    assert (qs[:, 0, :] == want[:, 1:5]).all()
+    bad = np.nonzero((p25[:, 0, :] != want[:, 5:30]).any(axis=1))[0]
+    assert len(bad) == 0, (len(bad), int(wpos[bad[0]]), int(wn[bad[0]]), p25[bad[0], 0], want[bad[0], 5:30])
+    assert eng.gl_rng_draws - d0 == int((wn[wn > 255] - 1).sum())
+    # the text path on the same deep columns (thousands of entries per line)
+    _same(eng.mpileup_text(), subprocess.run([oracle_bin, 'mpileup', '-B', '-f', fa, sam], capture_output=True, check=True).stdout, 'mpileup -B -f (C4 panel)')
+
+
+# ---------------------------------------------------------------- region shards with halo == unsharded (SURVEY 8e)
+def _shard_outputs(soa, L, n_shards, devices):
+    """stage the `-r` window of every shard (reads overlapping it: the halo) and run the three column stages on it"""
+    from samtools_b200 import engine, shard
+    mp, dp, cv, nsel = [], [], None, 0
+    for k, (beg, end) in enumerate(shard.plan_shards(L, n_shards)):
+        e = engine.Engine(devices[k % len(devices)])
+        w = shard.select_window(soa, beg, end)
+        e.stage(w, engine.default_stage_conf(engine.MODE_MPILEUP, beg=beg, end=end))
+        mp.append(e.mpileup_text(all=1))
+        e.stage(w, engine.default_stage_conf(engine.MODE_DEPTH, beg=beg, end=end))
+        dp.append(e.depth_text(all=1))
+        e.stage(w, engine.default_stage_conf(engine.MODE_COVERAGE, rflag_filter=4 | 256 | 512 | 1024, beg=beg, end=end))
+        s = e.coverage(min_baseQ=0, min_depth=1)
+        cv = s if cv is None else {k_: cv[k_] + s[k_] for k_ in s}
+        e.close()
+    return b''.join(mp), b''.join(dp), cv
+
+
+@pytest.mark.parametrize('n_shards', [2, 5])
+def test_region_shards_concatenate_to_unsharded(n_shards, tmp_path, oracle_bin):
+    """N shards of ONE contig, each staged with the reads that overlap it (bam_plcmd.c:550-554) and clipped to its columns
+    (:609): the concatenation is byte-identical to the unsharded run (mpileup -a -f with BAQ and the overlap tweak,
+    depth -a) and the coverage sums add up.  Runs sequentially on one GPU and, when the box has several, one shard per device."""
+    import torch
+    from samtools_b200 import engine, synth
+    L = 300_000
+    soa = synth.make_batch(length=L, depth=30, seed=5)
+    sam, fa = str(tmp_path / 's.sam'), str(tmp_path / 's.fa')
+    synth.write_sam(sam, soa); synth.write_fasta(fa, soa['tid_name'], soa['ref_full'])
+    want_mp = subprocess.run([oracle_bin, 'mpileup', '-a', '-f', fa, sam], capture_output=True, check=True).stdout
+    want_dp = subprocess.run([oracle_bin, 'depth', '-a', sam], capture_output=True, check=True).stdout
+    e = engine.Engine(0)
+    e.stage(soa, engine.default_stage_conf(engine.MODE_COVERAGE, rflag_filter=4 | 256 | 512 | 1024, end=L))
+    want_cv = e.coverage(min_baseQ=0, min_depth=1)
+    e.close()
+    dev_sets = [[0]]
+    if torch.cuda.device_count() > 1:
+        dev_sets.append(list(range(min(torch.cuda.device_count(), n_shards))))
+    for devs in dev_sets:
+        mp, dp, cv = _shard_outputs(soa, L, n_shards, devs)
+        _same(mp, want_mp, f'mpileup -a -f, {n_shards} shards on devices {devs}')
+        _same(dp, want_dp, f'depth -a, {n_shards} shards on devices {devs}')
+        assert cv == want_cv
+
+
 # ---------------------------------------------------------------- htslib-compatible iterator tier (T1)
 COMPAT = os.path.join(ROOT, 'tests', 'compat', '_build', 'plp_dump')
 
