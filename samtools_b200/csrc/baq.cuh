@@ -21,6 +21,7 @@
 // row sums run as a lane-uniform loop over a per-warp shared-memory copy of the row.  The forward matrix
 // lives in an HBM slab per resident warp (L2-resident); backward keeps two rows.
 #pragma once
+#include "baq_reg.h"
 
 struct BaqPlan { int64_t xb; int32_t l_ref, bw; };
 
@@ -77,7 +78,7 @@ __global__ void k_baq_plan(RawSoA r, b200_stage_conf_t cf, const uint8_t *state,
     if (b2 < d2) b2 = (int)d2;
     BaqPlan p; p.xb = xb; p.l_ref = (int32_t)l_ref; p.bw = b2;
     plan[i] = p;
-    if (use_tpr && b2 <= TPR_BW && lq <= TPR_MAX_LQ) {     // common shape: one thread per read (k_baq_tpr)
+    if (use_tpr == 2 ? (b2 == baqr::BW && lq <= TPR_MAX_LQ) : (use_tpr && b2 <= TPR_BW && lq <= TPR_MAX_LQ)) {     // common shape: one thread per read
         const unsigned long long slot2 = atomicAdd(&counters[3], 1ULL);
         idx2[slot2] = (int32_t)i;
         atomicMax(&counters[4], (unsigned long long)lq);
@@ -569,20 +570,85 @@ __global__ void __launch_bounds__(128, 8) k_baq_tpr(RawSoA r, const BaqPlan *pla
 #undef TS
 #undef TI
 
-// host: tables with the box's own libm (what the reference binary would use here)
-static void baq_host_tables(double *q2p, double *qthr)
+// ---------------------------------------------------------------------------------------------
+// Register-band BAQ (baq_reg.h): one thread per read of band 7, the band row in registers.  Per row a thread
+// writes the scaled forward M/I states (15 x 16 B) and the row's 1/s (8 B) into its lane's column of the warp's
+// slab -- slot s of row i of lane l lives at ((i-1)*16 + s)*32 + l (16-byte units), so a warp store is one
+// contiguous 512-byte request -- and reads them back once, in reverse, through cp.async into a double-buffered
+// per-thread shared-memory stage one row ahead of the MAP step that consumes them.
+struct BaqDevMem {
+    double2 *rows;             // this lane's slot 0 of row 1
+    int32_t *words;            // this lane's per-base scratch word 0
+    double2 *stage;            // this thread's slot 0 of stage buffer 0 (shared memory)
+    const uint8_t *refc; int64_t ref_lo, ref_n;
+    __device__ __forceinline__ int ref_code(int p) const { const int64_t a = ref_lo + p; return (a >= 0 && a < ref_n) ? (int)refc[a] : 4; }
+    __device__ __forceinline__ void put_row(int i, const double (&M)[baqr::NB], const double (&I)[baqr::NB], double inv)
+    {
+        double2 *r = rows + (size_t)(i - 1) * (16 * 32);
+#pragma unroll
+        for (int j = 0; j < baqr::NB; ++j) r[j * 32] = make_double2(M[j], I[j]);
+        reinterpret_cast<double *>(r + 15 * 32)[0] = inv;
+    }
+    __device__ __forceinline__ void fence() { __threadfence_block(); }
+    __device__ __forceinline__ void fetch(int i)
+    {
+        const double2 *r = rows + (size_t)(i - 1) * (16 * 32);
+        const uint32_t s = (uint32_t)__cvta_generic_to_shared(stage + (i & 1) * (16 * 128));
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s + k * (128 * 16)), "l"(r + k * 32) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void wait(int pending)
+    {
+        if (pending) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __device__ __forceinline__ void get(int i, int j, double &a, double &b) const { const double2 v = stage[((i & 1) * 16 + j) * 128]; a = v.x; b = v.y; }
+    __device__ __forceinline__ double inv(int i) const { return stage[((i & 1) * 16 + 15) * 128].x; }
+    __device__ __forceinline__ void put_word(int j, int32_t w) { words[(size_t)j * 32] = w; }
+    __device__ __forceinline__ int32_t get_word(int j) const { return words[(size_t)j * 32]; }
+};
+
+// reference bases -> 0..3 / 4 (ambiguous), once per staged reference
+__global__ void k_ref_codes(const char *ref, int64_t n, uint8_t *codes)
 {
-    for (int i = 0; i < 256; ++i) q2p[i] = pow(10, -i / 10.);
-    // qthr[j], j=1..101: the largest x in (0,1] with (int)(-4.343*log(x)+.499) >= j
-    qthr[0] = 2.0;
-    for (int j = 1; j <= 101; ++j) {
-        double x = exp(-((double)j - .499) / 4.343);
-        auto val = [](double v) { return (int)(-4.343 * log(v) + .499); };
-        while (x > 0 && val(x) < j) x = nextafter(x, 0.0);
-        while (true) { double nx = nextafter(x, 2.0); if (nx <= 1.0 && val(nx) >= j) x = nx; else break; }
-        qthr[j] = x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) codes[i] = (uint8_t)nt16_int_of(nt16_of((unsigned char)ref[i]));
+}
+
+constexpr int BAQR_THREADS = 128;
+constexpr int BAQR_STAGE_BYTES = 2 * 16 * BAQR_THREADS * 16;
+
+__global__ void __launch_bounds__(BAQR_THREADS, 3) k_baq_reg(RawSoA r, const BaqPlan *plan, const int32_t *idx, int64_t n_idx, double2 *slabs,
+                                                             unsigned long long slab_units, int lqmax, const uint8_t *refc,
+                                                             const double *q2p, const double *qthr)
+{
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ double s_q2pf[256];
+    __shared__ double s_qthr[102];
+    for (int t = threadIdx.x; t < 256; t += BAQR_THREADS) s_q2pf[t] = (double)(float)q2p[t];
+    for (int t = threadIdx.x; t < 102; t += BAQR_THREADS) s_qthr[t] = qthr[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_thr = (int64_t)gridDim.x * blockDim.x;
+    BaqDevMem mem;
+    mem.rows = slabs + (size_t)gw * slab_units + lane;
+    mem.words = reinterpret_cast<int32_t *>(slabs + (size_t)gw * slab_units + (size_t)lqmax * (16 * 32)) + lane;
+    mem.stage = reinterpret_cast<double2 *>(s_dyn) + threadIdx.x;
+    mem.refc = refc; mem.ref_n = r.ref_n;
+    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_idx; wi += n_thr) {
+        const int64_t ri = idx[wi];
+        const BaqPlan pl = plan[ri];
+        mem.ref_lo = pl.xb - r.ref_beg;
+        baqr::baq_read(mem, r.qual + r.qual_off[ri], r.seq4, (uint32_t)r.qual_off[ri], r.l_qseq[ri], pl.l_ref, r.pos[ri], pl.xb,
+                       r.cigar + r.cigar_off[ri], (int)r.n_cigar[ri], s_q2pf, s_qthr);
     }
 }
+
+// host: tables with the box's own libm (what the reference binary would use here)
+static void baq_host_tables(double *q2p, double *qthr) { baqr::host_tables(q2p, qthr); }
 
 int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
 {
@@ -601,7 +667,9 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
     if (ensure(e, e->baq_idx, e->cap_baq_idx, (size_t)(2 * nr) + plan_bytes / 4 + 4)) return -1;
     int32_t *idx = e->baq_idx, *idx2 = e->baq_idx + nr;
     BaqPlan *plan = (BaqPlan *)(e->baq_idx + 2 * nr);
-    static const int use_tpr = getenv("B200_BAQ_TPR") ? atoi(getenv("B200_BAQ_TPR")) : 1;
+    // 2 (default): band-7 reads on the register kernel (k_baq_reg), everything else on the warp kernel;
+    // 1: the round-1 thread-per-read kernel with its matrices in HBM (k_baq_tpr); 0: warp kernel only
+    static const int use_tpr = getenv("B200_BAQ_TPR") ? atoi(getenv("B200_BAQ_TPR")) : 2;
     CK(cudaMemsetAsync(e->d_misc + 16, 0, 16 * 8, e->stream));
     k_baq_plan<<<nblk(n, 256), 256, 0, e->stream>>>(r, cf, e->state, plan, idx, idx2, use_tpr, e->d_misc + 16); e->launches++;
     unsigned long long h[5];
@@ -609,7 +677,25 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
     const int64_t n_idx = (int64_t)h[0], n_idx2 = (int64_t)h[3];
-    if (n_idx2 > 0) {   // common shape: one thread per read
+    if (n_idx2 > 0 && use_tpr == 2) {   // band 7: one thread per read, band row in registers
+        const int lqmax = (int)h[4];
+        if (ensure(e, e->ref_codes, e->cap_ref_codes, (size_t)r.ref_n + 1)) return -1;
+        k_ref_codes<<<nblk(r.ref_n, 256), 256, 0, e->stream>>>(r.ref, r.ref_n, e->ref_codes); e->launches++;
+        // per warp: lqmax rows of 16 slots x 32 lanes x 16 B, then one scratch word per base and lane
+        const unsigned long long slab_units = (unsigned long long)lqmax * (16 * 32) + ((unsigned long long)lqmax * 32 * 4 + 15) / 16 + 32;
+        int64_t warps = (int64_t)e->n_sm * 3 * (BAQR_THREADS / 32);
+        const int64_t cap = (int64_t)((24ULL << 30) / (slab_units * 16));
+        if (warps > cap) warps = cap;
+        if (warps > (n_idx2 + 31) / 32) warps = (n_idx2 + 31) / 32;
+        if (warps < 1) warps = 1;
+        const int blocks = (int)((warps + BAQR_THREADS / 32 - 1) / (BAQR_THREADS / 32));
+        warps = (int64_t)blocks * (BAQR_THREADS / 32);
+        if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab_units * 2)) return -1;
+        static bool attr_set = false;
+        if (!attr_set) { CK(cudaFuncSetAttribute(k_baq_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, BAQR_STAGE_BYTES)); attr_set = true; }
+        k_baq_reg<<<blocks, BAQR_THREADS, BAQR_STAGE_BYTES, e->stream>>>(r, plan, idx2, n_idx2, (double2 *)e->baq_f, slab_units, lqmax, e->ref_codes, e->d_q2p, e->d_qthr); e->launches++;
+        CK(cudaGetLastError());
+    } else if (n_idx2 > 0) {   // round-1 thread-per-read kernel
         const int lqmax = (int)h[4];
         const unsigned long long slab = ((unsigned long long)(lqmax + 3) * TPR_PITCH + (unsigned long long)(lqmax + 2) + (5ULL * lqmax + 1) / 2 + 4) * 32;
         int64_t warps = (int64_t)e->n_sm * 32;
