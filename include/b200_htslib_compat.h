@@ -120,6 +120,34 @@ int b200_plp_insertion(const bam_pileup1_t *p, char *ins, int ins_cap, int *del_
 typedef struct kstring_t { size_t l, m; char *s; } kstring_t;
 int bam_plp_insertion(const bam_pileup1_t *p, kstring_t *ins, int *del_len);
 
+/* ---- per-read and per-column entry points of the same hot path (samtools_b200/csrc/host/hts_read_ops.cpp) ----------
+ * htslib realn.c:  sam_prob_realn (BAQ; call sites bam_plcmd.c:451, bam_md.c:475), sam_cap_mapq (bam_plcmd.c:453, bam_md.c:481)
+ * htslib errmod.h: errmod_init / errmod_cal / errmod_destroy (bam2bcf.c:46,121; phase.c:754; cut_target.c:84)
+ * bam2bcf.h:51-53: bcf_call_init / bcf_call_glfgen / bcf_call_destroy (tv_pl_func, bam_tview.c:193-205)
+ * htslib sam.h:    bam_plp_insertion_mod (pileup_seq, bam_plcmd.c:119; m == NULL, i.e. without -M markup)
+ * Same signatures, return codes and in-place effects as upstream; each call runs one small batch on the device. */
+int sam_prob_realn(bam1_t *b, const char *ref, hts_pos_t ref_len, int flag);   /* flag: 1 apply, 2 extend, 4 redo */
+int sam_cap_mapq(bam1_t *b, const char *ref, hts_pos_t ref_len, int thres);
+typedef struct errmod_t errmod_t;
+errmod_t *errmod_init(double depcorr);
+void errmod_destroy(errmod_t *em);
+int errmod_cal(const errmod_t *em, int n, int m, uint16_t *bases, float *q);
+typedef struct __bcf_callaux_t {          /* bam2bcf.h:33-39 */
+    int capQ, min_baseQ;
+    int max_bases;
+    uint16_t *bases;
+    errmod_t *e;
+} bcf_callaux_t;
+typedef struct {                          /* bam2bcf.h:42-45 */
+    float qsum[4];
+    float p[25];
+} bcf_callret1_t;
+bcf_callaux_t *bcf_call_init(double theta, int min_baseQ);
+void bcf_call_destroy(bcf_callaux_t *bca);
+int bcf_call_glfgen(int _n, const bam_pileup1_t *pl, int ref_base, bcf_callaux_t *bca, bcf_callret1_t *r);
+typedef struct hts_base_mod_state hts_base_mod_state;
+int bam_plp_insertion_mod(const bam_pileup1_t *p, hts_base_mod_state *m, kstring_t *ins, int *del_len);
+
 bam1_t *bam_init1(void);
 void bam_destroy1(bam1_t *b);
 bam1_t *bam_copy1(bam1_t *dst, const bam1_t *src);

@@ -100,7 +100,7 @@ typedef struct {
     int32_t min_mq;          /* -q */
     int32_t no_orphan;       /* 1 unless -A */
     int32_t illumina13;      /* -6 */
-    int32_t baq;             /* 0 off, 1 = sam_prob_realn flag 3, 2 = flag 7 (-E); needs ref */
+    int32_t baq;             /* 0 off, 1 = sam_prob_realn flag 3, 2 = flag 7 (-E), 3 = flag 1 (APPLY without EXTEND: calmd -A); needs ref */
     int32_t capq_thres;      /* -C */
     int32_t overlaps;        /* read-pair overlap detection (off with -x) */
     int32_t max_depth;       /* -d (bam_mplp_set_maxcnt) */
@@ -183,6 +183,19 @@ int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *conf, b200_cover
  * HBM (device-only timing, like out == NULL of the text calls); *n_cols is then the number of candidate columns */
 int b200_glf(b200_engine_t *e, int32_t min_baseQ, int64_t *n_cols, int64_t *col_pos, int32_t *n_bases,
              float *qsum, float *p25, size_t cap_cols);
+/* htslib's per-column / per-read entry points on the device (tier T1 support; one column or one small batch per call):
+ *   b200_errmod_cal   errmod_cal(em, n, m, bases, q) of htslib errmod.c (callers bam2bcf.c:121, phase.c:754, cut_target.c:84):
+ *                     `bases` (q<<5|strand<<4|allele) is left sorted like the reference leaves it, q[m*m] receives the
+ *                     phred-scaled genotype likelihoods; depcorr = the errmod_init argument; n > 255 consumes n-1 draws of
+ *                     the handle's drand48 stream (b200_gl_rng_draws)
+ *   b200_glfgen       bcf_call_glfgen (bam2bcf.c:65-123) for one column: per read the base quality at qpos (0 past the
+ *                     read's end), mapq, 4-bit base (0xff past the end) and fl (bit 0: is_del | is_refskip | unmapped,
+ *                     bit 1: reverse strand); returns n like the reference (-1 when n_reads <= 0)
+ *   b200_cap_mapq     sam_cap_mapq (htslib realn.c; call bam_plcmd.c:453) of every read of the staged batch */
+int b200_errmod_cal(b200_engine_t *e, double depcorr, int32_t n, int32_t m, uint16_t *bases, float *q);
+int b200_glfgen(b200_engine_t *e, double depcorr, int32_t n_reads, const uint8_t *q, const uint8_t *mapq, const uint8_t *base4, const uint8_t *fl,
+                int32_t ref_base, int32_t min_baseQ, int32_t capQ, float *qsum, float *p25);
+int b200_cap_mapq(b200_engine_t *e, int32_t thres, int32_t *out, size_t n);
 /* qualities after the read stage (BAQ / overlap tweak), for inspection and the iterator tier */
 int b200_fetch_qual(b200_engine_t *e, uint8_t *qual, size_t cap);
 int b200_fetch_mapq_keep(b200_engine_t *e, uint8_t *mapq, uint8_t *keep, size_t n);

@@ -36,12 +36,15 @@ errmod_t *errmod_new(double depcorr)
         double le = log(e);
         double le1 = log(1.0 - e);
         for (n = 1; n <= 255; ++n) {
+            /* binomial tail ratio in LOG space, long double accumulators (htslib errmod.c cal_coef): the plain-space
+             * running sums underflow to 0/0 = NaN for the deep k of a high-quality column (n = 167, q = 40, k >= 100) */
             double *beta = em->beta + (q << 16 | n << 8);
-            double sum, sum1;
-            sum1 = sum = 0.0;
-            for (k = n; k >= 0; --k, sum1 = sum) {
-                sum = sum1 + expl(lC[n << 8 | k] + k * le + (n - k) * le1);
-                beta[k] = -10. / M_LN10 * logl(sum1 / sum);
+            long double sum, sum1;
+            sum1 = lC[n << 8 | n] + n * le;
+            beta[n] = HUGE_VAL;
+            for (k = n - 1; k >= 0; --k, sum1 = sum) {
+                sum = sum1 + log1pl(expl(lC[n << 8 | k] + k * le + (n - k) * le1 - sum1));
+                beta[k] = -10. / M_LN10 * (sum1 - sum);
             }
         }
     }

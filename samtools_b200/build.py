@@ -35,11 +35,11 @@ def _sources(d, exts):
 def build_engine(force=False, verbose=False):
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     srcs = _sources(CSRC, ('.cu', '.cuh', '.h')) + [os.path.join(ROOT, 'include', 'b200_pileup.h'), os.path.join(ROOT, 'include', 'b200_htslib_compat.h'),
-                                                    os.path.join(CSRC, 'host', 'plp_compat.cpp')]
+                                                    os.path.join(CSRC, 'host', 'plp_compat.cpp'), os.path.join(CSRC, 'host', 'hts_read_ops.cpp')]
     if force or _newer(LIB, srcs):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB, os.path.join(CSRC, 'engine.cu'),
-                                                                                os.path.join(CSRC, 'host', 'plp_compat.cpp')]
+                                                                                os.path.join(CSRC, 'host', 'plp_compat.cpp'), os.path.join(CSRC, 'host', 'hts_read_ops.cpp')]
         subprocess.run(cmd, check=True)
     return LIB
 
@@ -67,6 +67,21 @@ def build_compat_client(force=False):
     return exe
 
 
+def build_read_ops_client(force=False):
+    """tests/compat/read_ops_check: a client of the per-read / per-column htslib entry points (sam_prob_realn, sam_cap_mapq,
+    errmod_cal, bcf_call_glfgen) that compares every result with the oracle's restatement in-process (links liboracle.so:
+    test infrastructure; the product library does not)."""
+    src = os.path.join(ROOT, 'tests', 'compat', 'read_ops_check.cpp')
+    exe = os.path.join(ROOT, 'tests', 'compat', '_build', 'read_ops_check')
+    ora = os.path.join(ROOT, 'oracle', '_build')
+    if force or _newer(exe, [src, LIB, os.path.join(ora, 'liboracle.so'), os.path.join(ROOT, 'include', 'b200_htslib_compat.h')]):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.run(['g++', '-std=c++17', '-O2', '-g', '-Wall', '-I', os.path.join(ROOT, 'include'), '-o', exe, src,
+                        '-L' + os.path.dirname(LIB), '-lb200pileup', '-L' + ora, '-loracle',
+                        '-Wl,-rpath,$ORIGIN/../../../samtools_b200/lib', '-Wl,-rpath,$ORIGIN/../../../oracle/_build', '-lz', '-lm'], check=True)
+    return exe
+
+
 def build_oracle():
     subprocess.run(['make', '-s', '-C', os.path.join(ROOT, 'oracle')], check=True)
     return os.path.join(ROOT, 'oracle', '_build', 'plp_oracle')
@@ -77,6 +92,7 @@ def build_all(force=False, verbose=False):
     build_cli(force)
     build_compat_client(force)
     build_oracle()
+    build_read_ops_client(force)
 
 
 if __name__ == '__main__':

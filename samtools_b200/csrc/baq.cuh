@@ -36,11 +36,9 @@ __device__ __forceinline__ int ref_code(const RawSoA &r, int64_t p)
 }
 
 // which reads need the HMM, their reference window and band (sam_prob_realn prologue)
-constexpr int TPR_BW = 7;            // band of the thread-per-read kernel (the default band of sam_prob_realn)
-constexpr int TPR_PITCH = 52;        // doubles per row: (2*7+1)*3 + 6 = 51, padded
-constexpr int TPR_MAX_LQ = 512;
+constexpr int BAQR_MAX_LQ = 512;     // longest read the register-band kernel takes (its slab grows with the longest read)
 
-__global__ void k_baq_plan(RawSoA r, b200_stage_conf_t cf, const uint8_t *state, BaqPlan *plan, int32_t *idx, int32_t *idx2, int use_tpr,
+__global__ void k_baq_plan(RawSoA r, b200_stage_conf_t cf, const uint8_t *state, BaqPlan *plan, int32_t *idx, int32_t *idx2, int use_reg,
                            unsigned long long *counters /* [0]=count, [1]=max slab doubles, [2]=max lq, [3]=count2, [4]=max lq of list 2 */)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,7 +76,7 @@ __global__ void k_baq_plan(RawSoA r, b200_stage_conf_t cf, const uint8_t *state,
     if (b2 < d2) b2 = (int)d2;
     BaqPlan p; p.xb = xb; p.l_ref = (int32_t)l_ref; p.bw = b2;
     plan[i] = p;
-    if (use_tpr == 2 ? (b2 == baqr::BW && lq <= TPR_MAX_LQ) : (use_tpr && b2 <= TPR_BW && lq <= TPR_MAX_LQ)) {     // common shape: one thread per read
+    if (use_reg && b2 == baqr::BW && lq <= BAQR_MAX_LQ) {     // band 7 (every read whose aligned spans differ by <= 7): one thread per read, k_baq_reg
         const unsigned long long slot2 = atomicAdd(&counters[3], 1ULL);
         idx2[slot2] = (int32_t)i;
         atomicMax(&counters[4], (unsigned long long)lq);
@@ -101,7 +99,7 @@ __device__ __forceinline__ double emis(int rc, int qc, double ql)
 
 __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, const int32_t *idx, int64_t n_idx, double *slabs,
                                              unsigned long long slab_doubles, const double *q2p, const double *qthr,
-                                             unsigned long long *work)
+                                             unsigned long long *work, int extend)
 {
     // per-warp exchange rows: the ordered (sequential-in-k) parts read the band cells of the row from
     // shared memory (broadcast loads that pipeline) instead of one shuffle round trip per cell
@@ -342,11 +340,13 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
                     if (l > 0) {
                         for (int j = y; j < y + l; ++j)
                             bq[j] = ((stv[j] & 3) != 0 || (int64_t)(stv[j] >> 2) != x - pl.xb + (j - y)) ? 0 : qv[j];
-                        left[y] = bq[y];
-                        for (int j = y + 1; j < y + l; ++j) left[j] = bq[j] > left[j - 1] ? bq[j] : left[j - 1];
-                        rght[y + l - 1] = bq[y + l - 1];
-                        for (int j = y + l - 2; j >= y; --j) rght[j] = bq[j] > rght[j + 1] ? bq[j] : rght[j + 1];
-                        for (int j = y; j < y + l; ++j) bq[j] = left[j] < rght[j] ? left[j] : rght[j];
+                        if (extend) {
+                            left[y] = bq[y];
+                            for (int j = y + 1; j < y + l; ++j) left[j] = bq[j] > left[j - 1] ? bq[j] : left[j - 1];
+                            rght[y + l - 1] = bq[y + l - 1];
+                            for (int j = y + l - 2; j >= y; --j) rght[j] = bq[j] > rght[j + 1] ? bq[j] : rght[j + 1];
+                            for (int j = y; j < y + l; ++j) bq[j] = left[j] < rght[j] ? left[j] : rght[j];
+                        }
                     }
                     x += l; y += l;
                 } else if (op == OP_S || op == OP_I) { if (l > lq - y) l = lq - y; y += l; }
@@ -363,214 +363,6 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
 
 
 // ---------------------------------------------------------------------------------------------
-// Thread-per-read BAQ for the common shape (band <= 7, l_qseq <= 512).  The recurrences are the
-// scalar loops of probaln_glocal verbatim (same order of every product and sum, so bit-exact by
-// construction); what is GPU-specific is the storage: the forward matrix, the two backward rows
-// and the scaling vector of the 32 reads of a warp are interleaved read-minor ("cell (i,u) of
-// lane l" lives at ((i*PITCH+u)*32 + l)), so every load/store of a warp is one coalesced
-// 256-byte request even though each thread walks its own matrix.  Cells just outside the band
-// that the next row (or the same row's D chain) will look at are zeroed explicitly -- the role
-// calloc plays in the reference.  No shuffles, no redundant lanes: ~28x fewer warp-instructions
-// per read than the warp-per-read kernel, which remains the path for wide bands / long reads.
-#define TF(i, u) fb[((size_t)(i) * TPR_PITCH + (size_t)(u)) * 32]
-#define TBROW(rw, u) bb[((size_t)(rw) * TPR_PITCH + (size_t)(u)) * 32]
-#define TS(i) sbv[(size_t)(i) * 32]
-#define TI(arr, j) ib[((size_t)(arr) * lqmax + (size_t)(j)) * 32]
-#define TPR_SET_U(u, b, i, k) { int x_ = (i) - (b); x_ = x_ > 0 ? x_ : 0; (u) = ((k) - x_ + 1) * 3; }
-
-__global__ void __launch_bounds__(128, 8) k_baq_tpr(RawSoA r, const BaqPlan *plan, const int32_t *idx, int64_t n_idx, double *slabs,
-                                                 unsigned long long slab_doubles, int lqmax, const double *q2p, const double *qthr)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_thr = (int64_t)gridDim.x * blockDim.x;
-    double *slab = slabs + (size_t)gw * slab_doubles;
-    double *fb = slab + lane;                                                  // forward matrix, (lqmax+1) rows
-    double *bb = slab + (size_t)(lqmax + 1) * TPR_PITCH * 32 + lane;          // two backward rows
-    double *sbv = slab + (size_t)(lqmax + 3) * TPR_PITCH * 32 + lane;         // scaling factors s[0..lq+1]
-    int32_t *ib = (int32_t *)(slab + (size_t)(lqmax + 3) * TPR_PITCH * 32 + (size_t)(lqmax + 2) * 32) + lane;   // 5 int arrays of lqmax
-    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_idx; wi += n_thr) {
-        const int64_t ri = idx[wi];
-        const BaqPlan pl = plan[ri];
-        const int l_query = r.l_qseq[ri], l_ref = pl.l_ref, bw = pl.bw;
-        uint8_t *qual = r.qual + r.qual_off[ri];
-        const uint32_t qoff = (uint32_t)r.qual_off[ri];
-        const double cd = 0.001, ce = 0.1;
-        const double sM = 1. / (2 * l_query + 2), sI = sM;
-        double m[9];
-        m[0] = (1 - cd - cd) * (1 - sM); m[1] = m[2] = cd * (1 - sM);
-        m[3] = (1 - ce) * (1 - sI); m[4] = ce * (1 - sI); m[5] = 0.;
-        m[6] = 1 - ce; m[7] = 0.; m[8] = ce;
-        const double bM = (1 - cd) / l_ref, bI = cd / l_ref;
-        int i, k;
-        TS(0) = 1.;
-        /*** forward ***/
-        {   // row 1
-            double sum = 0.;
-            const int beg = 1, end = l_ref < bw + 1 ? l_ref : bw + 1;
-            const int qc = nt16_int_of(base4(r.seq4, qoff, 0));
-            const double q0 = (double)(float)q2p[qual[0]];
-            int u0; TPR_SET_U(u0, bw, 1, beg);
-            TF(1, u0 - 3) = 0.; TF(1, u0 - 2) = 0.; TF(1, u0 - 1) = 0.;
-            for (k = beg; k <= end; ++k) {
-                int u; TPR_SET_U(u, bw, 1, k);
-                const double e = emis(ref_code(r, pl.xb + k - 1), qc, q0);
-                const double a = e * bM, b = BAQ_EI * bI;
-                TF(1, u) = a; TF(1, u + 1) = b; TF(1, u + 2) = 0.;
-                sum += a + b;
-            }
-            { int u; TPR_SET_U(u, bw, 1, end); TF(1, u + 3) = 0.; TF(1, u + 4) = 0.; TF(1, u + 5) = 0.; }
-            TS(1) = sum;
-            for (k = beg; k <= end; ++k) { int u; TPR_SET_U(u, bw, 1, k); TF(1, u) /= sum; TF(1, u + 1) /= sum; TF(1, u + 2) /= sum; }
-        }
-        for (i = 2; i <= l_query; ++i) {
-            const int qyi = nt16_int_of(base4(r.seq4, qoff, i - 1));
-            const double qli = (double)(float)q2p[qual[i - 1]];
-            int beg = 1, end = l_ref, x;
-            x = i - bw; beg = beg > x ? beg : x;
-            x = i + bw; end = end < x ? end : x;
-            double sum = 0.;
-            int u0; TPR_SET_U(u0, bw, i, beg);
-            TF(i, u0 - 3) = 0.; TF(i, u0 - 2) = 0.; TF(i, u0 - 1) = 0.;
-            double pM = 0., pD = 0.;                    // fi[v01+0], fi[v01+2]: the cell to the left in this row (unscaled)
-            for (k = beg; k <= end; ++k) {
-                int u, v11, v10;
-                TPR_SET_U(u, bw, i, k); TPR_SET_U(v11, bw, i - 1, k - 1); TPR_SET_U(v10, bw, i - 1, k);
-                const double e = emis(ref_code(r, pl.xb + k - 1), qyi, qli);
-                const double M = e * (m[0] * TF(i - 1, v11) + m[3] * TF(i - 1, v11 + 1) + m[6] * TF(i - 1, v11 + 2));
-                const double I = BAQ_EI * (m[1] * TF(i - 1, v10) + m[4] * TF(i - 1, v10 + 1));
-                const double D = m[2] * pM + m[8] * pD;
-                TF(i, u) = M; TF(i, u + 1) = I; TF(i, u + 2) = D;
-                sum += M + I + D;
-                pM = M; pD = D;
-            }
-            { int u; TPR_SET_U(u, bw, i, end); TF(i, u + 3) = 0.; TF(i, u + 4) = 0.; TF(i, u + 5) = 0.; }
-            TS(i) = sum;
-            const double inv = 1. / sum;
-            for (k = beg; k <= end; ++k) { int u; TPR_SET_U(u, bw, i, k); TF(i, u) *= inv; TF(i, u + 1) *= inv; TF(i, u + 2) *= inv; }
-        }
-        double s_last;
-        {   // termination
-            double sum = 0.;
-            for (k = 1; k <= l_ref; ++k) {
-                int u; TPR_SET_U(u, bw, l_query, k);
-                if (u < 3 || u >= (bw * 2 + 1) * 3 + 3) continue;
-                int beg = 1, end = l_ref, x;
-                x = l_query - bw; beg = beg > x ? beg : x;
-                x = l_query + bw; end = end < x ? end : x;
-                if (l_query == 1) end = l_ref < bw + 1 ? l_ref : bw + 1;
-                if (k < beg || k > end) continue;          // cells never written hold zero in the reference: adding 0 changes nothing
-                sum += TF(l_query, u) * sM + TF(l_query, u + 1) * sI;
-            }
-            s_last = sum;
-            TS(l_query + 1) = sum;
-        }
-        /*** backward + MAP ***/
-        int cur = 0;                                      // row buffer holding row i; 1-cur holds row i+1
-        {
-            const double s_lq = TS(l_query);
-            int beg = 1, end = l_ref, x;
-            x = l_query - bw; beg = beg > x ? beg : x;
-            x = l_query + bw; end = end < x ? end : x;
-            if (l_query == 1) end = l_ref < bw + 1 ? l_ref : bw + 1;
-            int u0; TPR_SET_U(u0, bw, l_query, beg);
-            TBROW(cur, u0 - 3) = 0.; TBROW(cur, u0 - 2) = 0.; TBROW(cur, u0 - 1) = 0.;
-            for (k = beg; k <= end; ++k) {
-                int u; TPR_SET_U(u, bw, l_query, k);
-                TBROW(cur, u) = sM / s_lq / s_last; TBROW(cur, u + 1) = sI / s_lq / s_last; TBROW(cur, u + 2) = 0.;
-            }
-            { int u; TPR_SET_U(u, bw, l_query, end); TBROW(cur, u + 3) = 0.; TBROW(cur, u + 4) = 0.; TBROW(cur, u + 5) = 0.; }
-        }
-        for (i = l_query; i >= 1; --i) {
-            int beg = 1, end = l_ref, x;
-            x = i - bw; beg = beg > x ? beg : x;
-            x = i + bw; end = end < x ? end : x;
-            if (i < l_query) {
-                const int nxt = cur; cur = 1 - cur;          // nxt holds row i+1
-                const double y = (i > 1) ? 1. : 0.;
-                const int qyi1 = nt16_int_of(base4(r.seq4, qoff, i));
-                const double qli1 = (double)(float)q2p[qual[i]];
-                { int u; TPR_SET_U(u, bw, i, end); TBROW(cur, u + 3) = 0.; TBROW(cur, u + 4) = 0.; TBROW(cur, u + 5) = 0.; }
-                double nD = 0.;                              // bi[v01+2]: D of the cell to the right in this row (already times y)
-                for (k = end; k >= beg; --k) {
-                    int u, v11, v10;
-                    TPR_SET_U(u, bw, i, k); TPR_SET_U(v11, bw, i + 1, k + 1); TPR_SET_U(v10, bw, i + 1, k);
-                    const double e = (k >= l_ref ? 0. : emis(ref_code(r, pl.xb + k), qyi1, qli1)) * TBROW(nxt, v11);
-                    const double b10 = TBROW(nxt, v10 + 1);
-                    const double B0 = e * m[0] + BAQ_EI * m[1] * b10 + m[2] * nD;
-                    const double B1 = e * m[3] + BAQ_EI * m[4] * b10;
-                    const double B2 = (e * m[6] + m[8] * nD) * y;
-                    TBROW(cur, u) = B0; TBROW(cur, u + 1) = B1; TBROW(cur, u + 2) = B2;
-                    nD = B2;
-                }
-                { int u; TPR_SET_U(u, bw, i, beg); TBROW(cur, u - 3) = 0.; TBROW(cur, u - 2) = 0.; TBROW(cur, u - 1) = 0.; }
-                const double ys = 1. / TS(i);
-                for (k = beg; k <= end; ++k) { int u; TPR_SET_U(u, bw, i, k); TBROW(cur, u) *= ys; TBROW(cur, u + 1) *= ys; TBROW(cur, u + 2) *= ys; }
-            }
-            // MAP of row i
-            double sum = 0., mx = 0.; int max_k = -1;
-            const int fend = (i == 1) ? (l_ref < bw + 1 ? l_ref : bw + 1) : end;
-            for (k = beg; k <= end; ++k) {
-                int u; TPR_SET_U(u, bw, i, k);
-                const bool inF = k <= fend;
-                double z = (inF ? TF(i, u) : 0.) * TBROW(cur, u);
-                if (z > mx) { mx = z; max_k = (k - 1) << 2 | 0; }
-                sum += z;
-                z = (inF ? TF(i, u + 1) : 0.) * TBROW(cur, u + 1);
-                if (z > mx) { mx = z; max_k = (k - 1) << 2 | 1; }
-                sum += z;
-            }
-            mx /= sum;
-            TI(0, i - 1) = max_k;
-            const double xx = 1. - mx;
-            int kq;
-            if (!(xx > 0.)) kq = 0;
-            else {
-                int lo_ = 0, hi_ = 101;
-                while (lo_ < hi_) { const int mid = (lo_ + hi_ + 1) >> 1; if (xx <= qthr[mid]) lo_ = mid; else hi_ = mid - 1; }
-                kq = lo_ > 100 ? 99 : lo_;
-            }
-            TI(1, i - 1) = kq;
-        }
-        // ---- sam_prob_realn epilogue (EXTEND + APPLY)
-        {
-            const int lq = l_query;
-            for (int j = 0; j < lq; ++j) TI(2, j) = qual[j];
-            const uint32_t *cg = r.cigar + r.cigar_off[ri];
-            int64_t x = r.pos[ri]; int y = 0;
-            for (int kk = 0; kk < (int)r.n_cigar[ri]; ++kk) {
-                const int op = cg[kk] & 0xf; int l = (int)(cg[kk] >> 4);
-                if (is_mop(op)) {
-                    if (l > lq - y) l = lq - y;
-                    if (l > 0) {
-                        for (int j = y; j < y + l; ++j) {
-                            const int st = TI(0, j);
-                            TI(2, j) = ((st & 3) != 0 || (int64_t)(st >> 2) != x - pl.xb + (j - y)) ? 0 : TI(1, j);
-                        }
-                        TI(3, y) = TI(2, y);
-                        for (int j = y + 1; j < y + l; ++j) { const int a = TI(2, j), b = TI(3, j - 1); TI(3, j) = a > b ? a : b; }
-                        TI(4, y + l - 1) = TI(2, y + l - 1);
-                        for (int j = y + l - 2; j >= y; --j) { const int a = TI(2, j), b = TI(4, j + 1); TI(4, j) = a > b ? a : b; }
-                        for (int j = y; j < y + l; ++j) { const int a = TI(3, j), b = TI(4, j); TI(2, j) = a < b ? a : b; }
-                    }
-                    x += l; y += l;
-                } else if (op == OP_S || op == OP_I) { if (l > lq - y) l = lq - y; y += l; }
-                else if (op == OP_D) x += l;
-            }
-            for (int j = 0; j < lq; ++j) {
-                const int qv = qual[j], bq = TI(2, j);
-                const int adj = qv <= bq ? 0 : qv - bq;
-                qual[j] = (uint8_t)(qv - adj);
-            }
-        }
-    }
-}
-#undef TF
-#undef TBROW
-#undef TS
-#undef TI
-
-// ---------------------------------------------------------------------------------------------
 // Register-band BAQ (baq_reg.h): one thread per read of band 7, the band row in registers.  Per row a thread
 // writes the scaled forward M/I states (15 x 16 B) and the row's 1/s (8 B) into its lane's column of the warp's
 // slab -- slot s of row i of lane l lives at ((i-1)*16 + s)*32 + l (16-byte units), so a warp store is one
@@ -581,7 +373,7 @@ struct BaqDevMem {
     int32_t *words;            // this lane's per-base scratch word 0
     double2 *stage;            // this thread's slot 0 of stage buffer 0 (shared memory)
     const uint8_t *refc; int64_t ref_lo, ref_n;
-    __device__ __forceinline__ int ref_code(int p) const { const int64_t a = ref_lo + p; return (a >= 0 && a < ref_n) ? (int)refc[a] : 4; }
+    __device__ __forceinline__ int ref_code(int p) const { const int64_t a = ref_lo + p; return (a >= 0 && a < ref_n) ? (int)(refc[a] >> 4) : 4; }
     __device__ __forceinline__ void put_row(int i, const double (&M)[baqr::NB], const double (&I)[baqr::NB], double inv)
     {
         double2 *r = rows + (size_t)(i - 1) * (16 * 32);
@@ -610,11 +402,12 @@ struct BaqDevMem {
     __device__ __forceinline__ int32_t get_word(int j) const { return words[(size_t)j * 32]; }
 };
 
-// reference bases -> 0..3 / 4 (ambiguous), once per staged reference
+// reference bases -> codes, once per staged reference: low nibble = 4-bit IUPAC code (what pileup_seq compares a
+// read base with), high nibble = 0..3 / 4 (ambiguous) (what the BAQ HMM compares)
 __global__ void k_ref_codes(const char *ref, int64_t n, uint8_t *codes)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) codes[i] = (uint8_t)nt16_int_of(nt16_of((unsigned char)ref[i]));
+    if (i < n) { const int c16 = nt16_of((unsigned char)ref[i]); codes[i] = (uint8_t)(c16 | nt16_int_of(c16) << 4); }
 }
 
 constexpr int BAQR_THREADS = 128;
@@ -622,7 +415,7 @@ constexpr int BAQR_STAGE_BYTES = 2 * 16 * BAQR_THREADS * 16;
 
 __global__ void __launch_bounds__(BAQR_THREADS, 3) k_baq_reg(RawSoA r, const BaqPlan *plan, const int32_t *idx, int64_t n_idx, double2 *slabs,
                                                              unsigned long long slab_units, int lqmax, const uint8_t *refc,
-                                                             const double *q2p, const double *qthr)
+                                                             const double *q2p, const double *qthr, int extend)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ double s_q2pf[256];
@@ -643,7 +436,7 @@ __global__ void __launch_bounds__(BAQR_THREADS, 3) k_baq_reg(RawSoA r, const Baq
         const BaqPlan pl = plan[ri];
         mem.ref_lo = pl.xb - r.ref_beg;
         baqr::baq_read(mem, r.qual + r.qual_off[ri], r.seq4, (uint32_t)r.qual_off[ri], r.l_qseq[ri], pl.l_ref, r.pos[ri], pl.xb,
-                       r.cigar + r.cigar_off[ri], (int)r.n_cigar[ri], s_q2pf, s_qthr);
+                       r.cigar + r.cigar_off[ri], (int)r.n_cigar[ri], s_q2pf, s_qthr, extend != 0);
     }
 }
 
@@ -667,20 +460,18 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
     if (ensure(e, e->baq_idx, e->cap_baq_idx, (size_t)(2 * nr) + plan_bytes / 4 + 4)) return -1;
     int32_t *idx = e->baq_idx, *idx2 = e->baq_idx + nr;
     BaqPlan *plan = (BaqPlan *)(e->baq_idx + 2 * nr);
-    // 2 (default): band-7 reads on the register kernel (k_baq_reg), everything else on the warp kernel;
-    // 1: the round-1 thread-per-read kernel with its matrices in HBM (k_baq_tpr); 0: warp kernel only
-    static const int use_tpr = getenv("B200_BAQ_TPR") ? atoi(getenv("B200_BAQ_TPR")) : 2;
+    // band-7 reads run on the register kernel (k_baq_reg), everything else (wide bands, very long reads) on the warp kernel;
+    // B200_BAQ_REG=0 sends every read to the warp kernel (cross-check)
+    static const int use_reg = getenv("B200_BAQ_REG") ? atoi(getenv("B200_BAQ_REG")) : 1;
     CK(cudaMemsetAsync(e->d_misc + 16, 0, 16 * 8, e->stream));
-    k_baq_plan<<<nblk(n, 256), 256, 0, e->stream>>>(r, cf, e->state, plan, idx, idx2, use_tpr, e->d_misc + 16); e->launches++;
+    k_baq_plan<<<nblk(n, 256), 256, 0, e->stream>>>(r, cf, e->state, plan, idx, idx2, use_reg, e->d_misc + 16); e->launches++;
     unsigned long long h[5];
     CK(cudaMemcpyAsync(h, e->d_misc + 16, sizeof h, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
     const int64_t n_idx = (int64_t)h[0], n_idx2 = (int64_t)h[3];
-    if (n_idx2 > 0 && use_tpr == 2) {   // band 7: one thread per read, band row in registers
+    if (n_idx2 > 0) {   // band 7: one thread per read, band row in registers
         const int lqmax = (int)h[4];
-        if (ensure(e, e->ref_codes, e->cap_ref_codes, (size_t)r.ref_n + 1)) return -1;
-        k_ref_codes<<<nblk(r.ref_n, 256), 256, 0, e->stream>>>(r.ref, r.ref_n, e->ref_codes); e->launches++;
         // per warp: lqmax rows of 16 slots x 32 lanes x 16 B, then one scratch word per base and lane
         const unsigned long long slab_units = (unsigned long long)lqmax * (16 * 32) + ((unsigned long long)lqmax * 32 * 4 + 15) / 16 + 32;
         int64_t warps = (int64_t)e->n_sm * 3 * (BAQR_THREADS / 32);
@@ -693,20 +484,7 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
         if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab_units * 2)) return -1;
         static bool attr_set = false;
         if (!attr_set) { CK(cudaFuncSetAttribute(k_baq_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, BAQR_STAGE_BYTES)); attr_set = true; }
-        k_baq_reg<<<blocks, BAQR_THREADS, BAQR_STAGE_BYTES, e->stream>>>(r, plan, idx2, n_idx2, (double2 *)e->baq_f, slab_units, lqmax, e->ref_codes, e->d_q2p, e->d_qthr); e->launches++;
-        CK(cudaGetLastError());
-    } else if (n_idx2 > 0) {   // round-1 thread-per-read kernel
-        const int lqmax = (int)h[4];
-        const unsigned long long slab = ((unsigned long long)(lqmax + 3) * TPR_PITCH + (unsigned long long)(lqmax + 2) + (5ULL * lqmax + 1) / 2 + 4) * 32;
-        int64_t warps = (int64_t)e->n_sm * 32;
-        const int64_t cap = (int64_t)((24ULL << 30) / (slab * 8));
-        if (warps > cap) warps = cap;
-        if (warps > (n_idx2 + 31) / 32) warps = (n_idx2 + 31) / 32;
-        if (warps < 1) warps = 1;
-        const int blocks = (int)((warps + 3) / 4);
-        warps = (int64_t)blocks * 4;
-        if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab)) return -1;
-        k_baq_tpr<<<blocks, 128, 0, e->stream>>>(r, plan, idx2, n_idx2, e->baq_f, slab, lqmax, e->d_q2p, e->d_qthr); e->launches++;
+        k_baq_reg<<<blocks, BAQR_THREADS, BAQR_STAGE_BYTES, e->stream>>>(r, plan, idx2, n_idx2, (double2 *)e->baq_f, slab_units, lqmax, e->ref_codes, e->d_q2p, e->d_qthr, cf.baq != 3); e->launches++;
         CK(cudaGetLastError());
     }
     if (n_idx > 0) {    // wide bands / long reads: one warp per read
@@ -720,7 +498,7 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
         warps = (int64_t)blocks * 4;
         if (n_idx2 > 0) CK(cudaStreamSynchronize(e->stream));   // the slab buffer is shared by the two kernels
         if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab)) return -1;
-        k_baq<<<blocks, 128, 0, e->stream>>>(r, plan, idx, n_idx, e->baq_f, slab, e->d_q2p, e->d_qthr, e->d_misc + 19 + 8); e->launches++;
+        k_baq<<<blocks, 128, 0, e->stream>>>(r, plan, idx, n_idx, e->baq_f, slab, e->d_q2p, e->d_qthr, e->d_misc + 19 + 8, cf.baq != 3); e->launches++;
     }
     CK(cudaGetLastError());
     return 0;

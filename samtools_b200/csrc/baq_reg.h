@@ -19,8 +19,8 @@
 // -ffp-contract=off); the sequential-in-k D recurrences and row sums stay sequential.  pow()/log() never run
 // on the device: host-libm tables (see baq.cuh).
 //
-// The arithmetic is __host__ __device__ so that tests/emul/baq_host.cpp can run it on the CPU against the
-// oracle's restatement (oracle/baq.c); memory traffic goes through a policy object (Mem).
+// The arithmetic is __host__ __device__ so that the test harness tests/emul/baq_host.cpp can single-step it on the
+// CPU against the CPU restatement of sam_prob_realn; memory traffic goes through a policy object (Mem).
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -119,7 +119,7 @@ PLP_HD int phred_of(double xx, const double *qthr)
 // q2pf[q] = (double)(float)pow(10, -q/10.)   qthr = break points (see baq.cuh)
 template <class Mem>
 PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff, int lq, int l_ref, int64_t pos, int64_t xb,
-                     const uint32_t *cg, int n_cigar, const double *q2pf, const double *qthr)
+                     const uint32_t *cg, int n_cigar, const double *q2pf, const double *qthr, bool extend = true)
 {
     const Par p = make_par(lq, l_ref);
     double M[NB], I[NB], D[NB];
@@ -214,8 +214,8 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         const int kq = phred_of(1. - mx, qthr);
         mem.put_word(i - 1, (int32_t)((uint32_t)max_k << 8 | (uint32_t)kq));
     }
-    // ---- sam_prob_realn epilogue (EXTEND + APPLY): per match run, zero the bases whose MAP state is not the
-    // aligned match, extend by the running maxima from both ends, cap the quality
+    // ---- sam_prob_realn epilogue (APPLY): per match run, zero the bases whose MAP state is not the aligned match,
+    // with EXTEND replace each by the smaller of the running maxima from both ends of the run, cap the quality
     int64_t x = pos; int y = 0;
     for (int kk = 0; kk < n_cigar; ++kk) {
         const int op = cg[kk] & 0xf; int l = (int)(cg[kk] >> 4);
@@ -227,14 +227,14 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
                     const int32_t w = mem.get_word(j);
                     const int st = w >> 8, kq = w & 0xff;
                     const int t = ((st & 3) != 0 || (int64_t)(st >> 2) != x - xb + (j - y)) ? 0 : kq;
-                    left = t > left ? t : left;
+                    left = (extend && left > t) ? left : t;
                     mem.put_word(j, t | left << 8);
                 }
                 int rght = 0;
                 for (int j = y + l - 1; j >= y; --j) {
                     const int32_t w = mem.get_word(j);
                     const int t = w & 0xff, lf = w >> 8;
-                    rght = t > rght ? t : rght;
+                    rght = (extend && rght > t) ? rght : t;
                     const int bq = lf < rght ? lf : rght;
                     const int qv = qual[j];
                     qual[j] = (uint8_t)(qv - (qv <= bq ? 0 : qv - bq));

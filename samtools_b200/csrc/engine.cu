@@ -8,7 +8,7 @@
 //               prev_same_name i64 | rbits u8          (one array per field)
 //   payload     cigar u32[] | seq4 u8[] (4-bit) | qual u8[] | ref char[]
 //   derived     ReadDesc[32 B] per read, prefix-max of read ends, per-32-column
-//               [lo,hi) read ranges, look-back status words, output text
+//               [lo,hi) read ranges, entry strings (2 B per read base), look-back status words, output text
 //
 // Column stage for text (mpileup, depth): sizes -> offsets -> bytes, no inter-CTA waiting.
 //   (1) a size pass gives every column its line length (mpileup: order-free streaming pass
@@ -123,20 +123,33 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_s
 
 // ============================== read stage ===================================
 // (arithmetic in plp_stage.h; one thread per read)
+// warp sum of a 64-bit quantity that is < 2^47 per lane: three redux.sync (16-bit limbs cannot overflow 32 lanes)
+__device__ __forceinline__ unsigned long long warp_sum_u48(unsigned long long v)
+{
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xffffu));
+    const unsigned mid = __reduce_add_sync(0xffffffffu, (unsigned)((v >> 16) & 0xffffu));
+    const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(v >> 32));
+    return (unsigned long long)lo + ((unsigned long long)mid << 16) + ((unsigned long long)hi << 32);
+}
 __device__ __forceinline__ void merge_acc(const StageAcc &a, StageAcc *g)
 {
-    unsigned long long v[8] = {a.n_kept, a.n_kept_in_window, a.sum_rlen, a.sum_indel_text, a.n_reads, a.n_selected, a.summed_mapq, a.n_desc};
-    int mx = a.max_rend;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
+    // per-lane values are tiny (a read contributes 0/1 to the counters, its span / text bound / mapq to the sums):
+    // single-instruction warp reductions instead of 64-bit shuffle trees (the trees cost ~180 issue slots per warp)
+    const unsigned n_kept = __reduce_add_sync(0xffffffffu, (unsigned)a.n_kept), n_win = __reduce_add_sync(0xffffffffu, (unsigned)a.n_kept_in_window);
+    const unsigned n_reads = __reduce_add_sync(0xffffffffu, (unsigned)a.n_reads), n_sel = __reduce_add_sync(0xffffffffu, (unsigned)a.n_selected);
+    const unsigned mq = __reduce_add_sync(0xffffffffu, (unsigned)a.summed_mapq), n_desc = __reduce_add_sync(0xffffffffu, (unsigned)a.n_desc);
+    const unsigned long long rl = warp_sum_u48(a.sum_rlen), it = warp_sum_u48(a.sum_indel_text), rg = warp_sum_u48(a.sum_rlen_gen);
+    const int mx = __reduce_max_sync(0xffffffffu, a.max_rend);
     if ((threadIdx.x & 31) == 0) {
-        unsigned long long *gp[8] = {&g->n_kept, &g->n_kept_in_window, &g->sum_rlen, &g->sum_indel_text, &g->n_reads, &g->n_selected, &g->summed_mapq, &g->n_desc};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (v[k]) atomicAdd(gp[k], v[k]);
+        if (n_kept) atomicAdd(&g->n_kept, (unsigned long long)n_kept);
+        if (n_win) atomicAdd(&g->n_kept_in_window, (unsigned long long)n_win);
+        if (rl) atomicAdd(&g->sum_rlen, rl);
+        if (it) atomicAdd(&g->sum_indel_text, it);
+        if (n_reads) atomicAdd(&g->n_reads, (unsigned long long)n_reads);
+        if (n_sel) atomicAdd(&g->n_selected, (unsigned long long)n_sel);
+        if (mq) atomicAdd(&g->summed_mapq, (unsigned long long)mq);
+        if (n_desc) atomicAdd(&g->n_desc, (unsigned long long)n_desc);
+        if (rg) atomicAdd(&g->sum_rlen_gen, rg);
         if (mx != INT32_MIN) atomicMax(&g->max_rend, mx);
     }
 }
@@ -295,65 +308,13 @@ __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uin
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-// Shared skeleton of the text-producing kernels.  Fmt provides
-//   uint32_t size(int32_t c, State&)   and   void write(int32_t c, const State&, char*)
-template <class Fmt>
-__device__ __forceinline__ void text_tile(const Fmt &fmt, int32_t ncols, char *out, uint64_t *status, uint32_t *ticket,
-                                          unsigned long long *total_out, uint32_t smem_cap, int use_tma)
-{
-    extern __shared__ __align__(16) char s_text[];
-    __shared__ uint32_t s_ws[TILE / 32];
-    __shared__ int s_tile;
-    __shared__ uint64_t s_base;
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
-    __syncthreads();
-    const int t = s_tile;
-    const int32_t c = t * TILE + (int32_t)threadIdx.x;
-    typename Fmt::State stt;
-    uint32_t len = c < ncols ? fmt.size(c, stt) : 0;
-    uint32_t total;
-    const uint32_t off = block_excl_scan<TILE>(len, s_ws, total);
-    if (threadIdx.x < 32) {
-        const uint64_t b = lookback_sum(status, t, total);
-        if (threadIdx.x == 0) { s_base = b; if (t == (int)gridDim.x - 1) *total_out = b + total; }
-    }
-    __syncthreads();
-    const uint64_t base = s_base;
-    if (total == 0) return;
-    const uint32_t phase = (uint32_t)(base & 15);
-    if (total + phase <= smem_cap) {
-        char *sb = s_text + phase;
-        if (len) fmt.write(c, stt, sb + off);
-        __syncthreads();
-        // ragged head (to the next 16 B boundary of the destination), aligned body, ragged tail
-        char *g = out + base;
-        const uint32_t head = min(total, (16u - phase) & 15u);
-        const uint32_t body = (total - head) & ~15u;
-        const uint32_t tail = total - head - body;
-        if (threadIdx.x < head) g[threadIdx.x] = sb[threadIdx.x];
-        if (threadIdx.x < tail) g[head + body + threadIdx.x] = sb[head + body + threadIdx.x];
-        if (body) {
-            if (use_tma) {
-                if (threadIdx.x == 0) bulk_store_s2g(g + head, sb + head, body);
-            } else {
-                const uint4 *src = reinterpret_cast<const uint4 *>(sb + head);
-                uint4 *dst = reinterpret_cast<uint4 *>(g + head);
-                for (uint32_t i = threadIdx.x; i < body / 16; i += TILE) dst[i] = src[i];
-            }
-        }
-    } else if (len) {
-        fmt.write(c, stt, out + base + off);   // very deep tile: format straight into HBM
-    }
-}
-
-// ---- two-launch variant: no inter-CTA dependency at all --------------------
+// ---- text kernels: no inter-CTA dependency at all ---------------------------
+// Fmt provides   uint32_t size(int32_t c, State&)   and   void write(int32_t c, const State&, char*)
 // (1) k_*_size: every thread sizes its line; per-column {len,state} and the
 //     tile total go to HBM (16-24 B per column, small next to the text itself);
 // (2) a scan of the tile totals gives each tile its byte offset;
 // (3) k_*_write: the tile formats its lines into shared memory, already laid
-//     out with the destination's 16-byte phase, and leaves through one TMA bulk
-//     store.  The chained single-launch variant above waits inside the kernel
-//     for predecessor tiles; this one never waits.
+//     out with the destination's 16-byte phase, and leaves through one TMA bulk store.
 template <class Fmt>
 __device__ __forceinline__ void text_size_tile(const Fmt &fmt, int32_t ncols, uint32_t *len_out, typename Fmt::State *st_out,
                                                uint32_t *tile_total)
@@ -417,12 +378,6 @@ struct MpFmt {
     __device__ __forceinline__ void write(int32_t c, const State &s, char *p) const { mp_line_write(v, cf, c >> 5, c, s, p); }
 };
 
-__global__ void __launch_bounds__(TILE) k_mpileup(MpFmt fmt, char *out, uint64_t *status, uint32_t *ticket,
-                                                  unsigned long long *total_out, uint32_t smem_cap, int use_tma)
-{
-    text_tile(fmt, fmt.v.ncols, out, status, ticket, total_out, smem_cap, use_tma);
-}
-
 __global__ void __launch_bounds__(TILE) k_mpileup_size(MpFmt fmt, uint32_t *len, MpFileSz *st, uint32_t *tile_total)
 {
     text_size_tile(fmt, fmt.v.ncols, len, st, tile_total);
@@ -432,32 +387,8 @@ __global__ void __launch_bounds__(TILE) k_mpileup_write(MpFmt fmt, const uint32_
 {
     text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
 }
-// opt-in (B200_PLP_LEAN=1): the lean per-read loop of plp_core.h::mp_line_write_lean (single file, no -s / -O columns).
-// Bit-exact against the goldens and the fuzz cases on the emulation harness; NOT yet run or timed on a GPU.
-struct MpLeanFmt {
-    View v; MpConf cf; const uint8_t *tab;
-    typedef MpFileSz State;
-    __device__ __forceinline__ void write(int32_t c, const State &s, char *p) const { mp_line_write_lean(v, cf, c, s, p, tab); }
-};
-__global__ void __launch_bounds__(TILE) k_mpileup_write_lean(MpLeanFmt fmt, const uint32_t *len, const MpFileSz *st, const uint64_t *tile_base,
-                                                             char *out, uint32_t smem_cap, int use_tma)
-{
-    __shared__ uint8_t s_tab[32];
-    if (threadIdx.x < 32) s_tab[threadIdx.x] = (uint8_t)".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn"[threadIdx.x];   // visible after the barriers of the tile scan
-    fmt.tab = s_tab;
-    text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
-}
-// same kernel compiled for 12 resident CTAs per SM (<= 40 registers): the loop is latency-bound, occupancy pays
-__global__ void __launch_bounds__(TILE, 12) k_mpileup_write_occ(MpFmt fmt, const uint32_t *len, const MpFileSz *st, const uint64_t *tile_base,
-                                                               char *out, uint32_t smem_cap, int use_tma)
-{
-    text_write_tile(fmt, fmt.v.ncols, len, st, tile_base, out, smem_cap, use_tma);
-}
-
-#include "mpileup_rm.cuh"
-#include "mpileup_w4.cuh"
 #include "mpileup_ss.cuh"
-#include "mpileup_sr.cuh"
+#include "mpileup_ent.cuh"
 
 // depth rows "name\tpos(\tdepth)*\n" (bam2depth.c:234-244)
 struct DpFmt {
@@ -490,12 +421,6 @@ struct DpFmt {
         *p = '\n';
     }
 };
-
-__global__ void __launch_bounds__(TILE) k_depth(DpFmt fmt, char *out, uint64_t *status, uint32_t *ticket,
-                                                unsigned long long *total_out, uint32_t smem_cap, int use_tma)
-{
-    text_tile(fmt, fmt.v.ncols, out, status, ticket, total_out, smem_cap, use_tma);
-}
 
 __global__ void __launch_bounds__(TILE) k_depth_size(DpFmt fmt, uint32_t *len, DpFmt::State *st, uint32_t *tile_total)
 {
@@ -651,24 +576,13 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     e->smem_text = 24 * 1024;
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
-    s = getenv("B200_PLP_CHAINED"); e->chained = s ? atoi(s) : 0;
-    s = getenv("B200_PLP_WRITE_OCC"); e->write_occ = s ? atoi(s) : 0;
-    s = getenv("B200_PLP_STREAM_SIZE"); e->stream_size = s ? atoi(s) : 1;
-    s = getenv("B200_PLP_SR"); e->sr_write = s ? atoi(s) : 0;
-    s = getenv("B200_PLP_LEAN"); e->lean_write = s ? atoi(s) : 0;
-    cudaFuncSetAttribute(k_mpileup_write_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
-    cudaFuncSetAttribute(k_mp_sr_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
-    cudaFuncSetAttribute(k_mpileup_write_occ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
-    s = getenv("B200_PLP_VARIANT"); e->variant = s ? atoi(s) : 0;   // 0: read-major sizing + one-column-per-thread write (default), 1: column-major both, 2: read-major both, 4: read-major sizing + 4-columns-per-thread write
-    if (e->chained) e->variant = 1;
-    e->smem_text_rm = 36 * 1024;
-    s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text_rm = (uint32_t)atoi(s);
-    cudaFuncSetAttribute(k_mp_rm_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text_rm + 16);
-    cudaFuncSetAttribute(k_mpileup_write4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text_rm + 16);
-    cudaFuncSetAttribute(k_mpileup_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
-    cudaFuncSetAttribute(k_depth_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
-    cudaFuncSetAttribute(k_mpileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
-    cudaFuncSetAttribute(k_depth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_text + 16);
+    s = getenv("B200_PLP_GENERAL"); e->general = s ? atoi(s) : 0;   // 1: general mpileup path (thread-per-column size + write) for every configuration
+    if (e->smem_text + 16 > 48 * 1024) {   // the attribute is per function and process-wide: only ever raise it (another handle may use more)
+        cudaFuncSetAttribute(k_mp_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_mpileup_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_depth_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e->smem_text > 200 * 1024 - 16) e->smem_text = 200 * 1024 - 16;
+    }
     cudaMalloc((void **)&e->d_acc, sizeof(StageAcc));
     cudaMalloc((void **)&e->d_misc, 64 * sizeof(unsigned long long));
     *out = e;
@@ -844,6 +758,10 @@ static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
     r.ref = e->has_ref ? e->ref : nullptr; r.ref_beg = e->ref_beg; r.ref_n = e->ref_n; r.ref_len = e->ref_len;
     r.n = n; r.tid = e->tid;
     StageAcc *acc = (StageAcc *)e->d_acc;
+    if (e->has_ref && e->ref_n > 0) {   // reference bases -> codes, once per staged batch (BAQ: 0..4, pileup_seq: nt16)
+        ENSURE(ref_codes, (size_t)e->ref_n + 1);
+        k_ref_codes<<<nblk(e->ref_n, 256), 256, 0, e->stream>>>(e->ref, e->ref_n, e->ref_codes); e->launches++;
+    }
     if (n > 0) {
         k_prep1<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, acc); e->launches++;
         e->baq_ran = false;
@@ -863,7 +781,7 @@ static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
     CK(cudaStreamSynchronize(e->stream));
     if (ha.n_desc) { const int rc = check_sorted_host(e, n); if (rc) return rc; }
     e->acc_n_kept = (int64_t)ha.n_kept; e->max_rend = ha.n_kept ? ha.max_rend : 0;
-    e->sum_rlen = ha.sum_rlen; e->sum_indel_text = ha.sum_indel_text;
+    e->sum_rlen = ha.sum_rlen; e->sum_indel_text = ha.sum_indel_text; e->sum_rlen_gen = ha.sum_rlen_gen;
     // ---- column domain
     {
         int64_t wend = cf->end - e->win_base;                       // exclusive, relative
@@ -1007,8 +925,8 @@ static int upload_bed(b200_engine *e, const int64_t *bb, const int64_t *be, int 
     return 0;
 }
 
-template <class Fmt, class K, class KS, class KW>
-static int run_text(b200_engine *e, K kernel, KS k_size, KW k_write, const Fmt &fmt, uint64_t bound, char *out, size_t out_cap, size_t *out_len)
+template <class Fmt, class KS, class KW>
+static int run_text(b200_engine *e, KS k_size, KW k_write, const Fmt &fmt, uint64_t bound, char *out, size_t out_cap, size_t *out_len)
 {
     const int32_t ncols = fmt.v.ncols;
     const int nt = (ncols + TILE - 1) / TILE;
@@ -1017,36 +935,30 @@ static int run_text(b200_engine *e, K kernel, KS k_size, KW k_write, const Fmt &
     if (nt == 0) return 0;
     ENSURE(out, (size_t)bound + 64);
     unsigned long long total = 0;
-    if (e->chained) {
-        ENSURE(status, (size_t)nt + 1);
-        CK(cudaMemsetAsync(e->status, 0, ((size_t)nt + 1) * 8, e->stream));
-        CK(cudaMemsetAsync(e->d_misc, 0, 16, e->stream));
-        CK(cudaEventRecord(e->ev0, e->stream));
-        kernel<<<nt, TILE, e->smem_text + 16, e->stream>>>(fmt, e->out, e->status, (uint32_t *)e->d_misc, e->d_misc + 1, e->smem_text, e->use_tma);
-        e->launches++;
-        CK(cudaEventRecord(e->ev1, e->stream));
-        CK(cudaMemcpyAsync(&total, e->d_misc + 1, 8, cudaMemcpyDeviceToHost, e->stream));
-    } else {
-        typedef typename Fmt::State State;
-        ENSURE(col_n, (size_t)ncols + 1);                                   // per-column line length
-        const size_t st_words = ((size_t)ncols * sizeof(State) + 7) / 8 + 1;
-        ENSURE(col_state, st_words);                                        // per-column formatter state
-        ENSURE(tile_total, (size_t)nt + 1); ENSURE(col_off, (size_t)nt + 2);
-        const int nb = nblk(nt, 256);
-        ENSURE(status, (size_t)nb + 1);
-        CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
-        CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
-        CK(cudaEventRecord(e->ev0, e->stream));
-        k_size<<<nt, TILE, 0, e->stream>>>(fmt, e->col_n, (State *)e->col_state, e->tile_total); e->launches++;
-        k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
-        k_write<<<nt, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const State *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
-        e->launches++;
-        CK(cudaEventRecord(e->ev1, e->stream));
-        CK(cudaMemcpyAsync(&total, e->col_off + nt, 8, cudaMemcpyDeviceToHost, e->stream));
-    }
+    typedef typename Fmt::State State;
+    ENSURE(col_n, (size_t)ncols + 1);                                   // per-column line length
+    const size_t st_words = ((size_t)ncols * sizeof(State) + 7) / 8 + 1;
+    ENSURE(col_state, st_words);                                        // per-column formatter state
+    ENSURE(tile_total, (size_t)nt + 1); ENSURE(col_off, (size_t)nt + 2);
+    const int nb = nblk(nt, 256);
+    ENSURE(status, (size_t)nb + 1);
+    CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
+    CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    k_size<<<nt, TILE, 0, e->stream>>>(fmt, e->col_n, (State *)e->col_state, e->tile_total); e->launches++;
+    CK(cudaEventRecord(e->evA, e->stream));
+    k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
+    CK(cudaEventRecord(e->evB, e->stream));
+    k_write<<<nt, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const State *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+    e->launches++;
+    CK(cudaEventRecord(e->ev1, e->stream));
+    CK(cudaMemcpyAsync(&total, e->col_off + nt, 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
+    cudaEventElapsedTime(&ms, e->ev0, e->evA); e->last_parts_ms[0] = ms;      // size pass
+    cudaEventElapsedTime(&ms, e->evA, e->evB); e->last_parts_ms[1] = ms;      // tile-offset scan
+    cudaEventElapsedTime(&ms, e->evB, e->ev1); e->last_parts_ms[2] = ms;      // write pass
     if (total > bound) { snprintf(e->err, sizeof e->err, "internal: output %llu exceeds bound %llu", total, (unsigned long long)bound); return -1; }
     *out_len = (size_t)total;
     e->last_out_len = (size_t)total;
@@ -1070,72 +982,56 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     fmt.cf.out_qpos5 = c->out_qpos5; fmt.cf.n_star_cols = c->n_star_cols;
     const int per = 2 + (c->out_mapq ? 1 : 0) + (c->out_qpos ? 12 : 0) + (c->out_qpos5 ? 13 : 0);
     const uint64_t bound = e->text_bound(per, 1 + 2 * (3 + c->n_star_cols)) ;
-    if (e->variant == 1) return run_text(e, k_mpileup, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
-    // ---- default: read-major sizing (coalesced along the reads), then a write kernel:
-    //      variant 0 = column-major write (thread per position), variant 2 = read-major write
+    if (e->general || e->n_files != 1 || c->out_qpos || c->out_qpos5)
+        return run_text(e, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
+    // ---- default (one input file, no -O columns): entry strings + gather (mpileup_ent.cuh)
     const int32_t ncols = fmt.v.ncols;
-    const int ntr = (ncols + RM_COLS - 1) / RM_COLS;     // read-major CTAs (256 columns)
-    const int nt = ntr * 2;                              // 128-column tiles of the offset scan
+    const int nt = (ncols + TILE - 1) / TILE;            // 128-column tiles
     *out_len = 0; e->last_kernel_ms = 0;
-    if (ntr == 0) return 0;
+    if (nt == 0) return 0;
     ENSURE(out, (size_t)bound + 64);
     ENSURE(col_n, (size_t)nt * TILE + 1);
-    ENSURE(col_state, ((size_t)nt * TILE * (size_t)e->n_files * sizeof(MpFileSz) + 7) / 8 + 1);
+    ENSURE(col_state, ((size_t)nt * TILE * sizeof(MpFileSz) + 7) / 8 + 1);
     ENSURE(tile_total, (size_t)nt + 1); ENSURE(col_off, (size_t)nt + 2);
+    ENSURE(ent, e->qual_bytes + 16); ENSURE(ent2, (size_t)e->sum_rlen_gen + 16);
     const int nb = nblk(nt, 256);
     ENSURE(status, (size_t)nb + 1);
     CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
     CK(cudaMemsetAsync(e->d_misc, 0, 8, e->stream));
+    ENSURE(ss_diff, (size_t)ncols + 2); ENSURE(ss_nplp, (size_t)ncols + 2); ENSURE(ss_fail, (size_t)ncols + 1); ENSURE(ss_extra, (size_t)ncols + 1);
+    CK(cudaMemsetAsync(e->ss_diff, 0, ((size_t)ncols + 2) * 4, e->stream));
+    CK(cudaMemsetAsync(e->ss_fail, 0, ((size_t)ncols + 1) * 4, e->stream));
+    CK(cudaMemsetAsync(e->ss_extra, 0, ((size_t)ncols + 1) * 4, e->stream));
+    const int nbs = nblk((int64_t)ncols + 1, 1024);
+    ENSURE(status2, (size_t)nbs + 1);
+    CK(cudaMemsetAsync(e->status2, 0, ((size_t)nbs + 1) * 8, e->stream));
+    CK(cudaMemsetAsync(e->d_misc + 2, 0, 16, e->stream));      // scan ticket, cursor of the second entry array
     CK(cudaEventRecord(e->ev0, e->stream));
-    if (e->stream_size && e->variant == 0 && e->n_files == 1 && !c->out_qpos && !c->out_qpos5) {
-        // order-free streaming size pass (mpileup_ss.cuh)
-        ENSURE(ss_diff, (size_t)ncols + 2); ENSURE(ss_nplp, (size_t)ncols + 2); ENSURE(ss_fail, (size_t)ncols + 1); ENSURE(ss_extra, (size_t)ncols + 1);
-        CK(cudaMemsetAsync(e->ss_diff, 0, ((size_t)ncols + 2) * 4, e->stream));
-        CK(cudaMemsetAsync(e->ss_fail, 0, ((size_t)ncols + 1) * 4, e->stream));
-        CK(cudaMemsetAsync(e->ss_extra, 0, ((size_t)ncols + 1) * 4, e->stream));
-        const int nbs = nblk((int64_t)ncols + 1, 1024);
-        ENSURE(status2, (size_t)nbs + 1);
-        CK(cudaMemsetAsync(e->status2, 0, ((size_t)nbs + 1) * 8, e->stream));
-        CK(cudaMemsetAsync(e->d_misc + 2, 0, 8, e->stream));
+    {
         const int64_t want_blocks = (e->n * 32 + 255) / 256;
         const int rb = (int)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)e->n_sm * 16));
-        k_ss_reads<<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, e->ss_diff, e->ss_fail, e->ss_extra); e->launches++;
+        k_mp_entries<<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, e->has_ref ? e->ref_codes : nullptr, e->ss_diff, e->ss_fail, e->ss_extra,
+                                                e->ent, e->ent2, e->d_misc + 3, e->desc); e->launches++;
         k_ss_scan<<<nbs, 256, 0, e->stream>>>(e->ss_diff, e->ss_nplp, ncols + 1, e->status2, (uint32_t *)(e->d_misc + 2)); e->launches++;
         k_ss_cols<<<nt, TILE, 0, e->stream>>>(fmt.v, fmt.cf, e->ss_nplp, e->ss_fail, e->ss_extra, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
-    } else {
-        k_mp_rm_size<<<ntr, RM_WARPS * 32, 0, e->stream>>>(fmt.v, fmt.cf, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
     }
     CK(cudaEventRecord(e->evA, e->stream));
     k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
     CK(cudaEventRecord(e->evB, e->stream));
-    if (e->variant == 2) {
-        k_mp_rm_write<<<ntr, RM_WARPS * 32, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
-                                                                              e->smem_text_rm, e->use_tma);
-    } else if (e->variant == 4 && e->n_files == 1 && !c->out_mapq && !c->out_qpos && !c->out_qpos5) {
-        // experimental: four adjacent columns per thread (fewer instructions per entry, but the 128 columns a warp
-        // stages in shared memory cap occupancy at ~14 warps/SM: measured slower than one column per thread)
-        k_mpileup_write4<<<ntr, W4_THREADS, e->smem_text_rm + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out,
-                                                                              e->smem_text_rm, e->use_tma);
-    } else {
-        const int ntw = (ncols + TILE - 1) / TILE;
-        if (e->sr_write && e->variant == 0 && e->n_files == 1 && !c->out_qpos && !c->out_qpos5)
-            k_mp_sr_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt.v, fmt.cf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
-        else if (e->lean_write && e->variant == 0 && e->n_files == 1 && !c->out_mapq && !c->out_qpos && !c->out_qpos5) {
-            MpLeanFmt lf; lf.v = fmt.v; lf.cf = fmt.cf; lf.tab = nullptr;
-            k_mpileup_write_lean<<<ntw, TILE, e->smem_text + 16, e->stream>>>(lf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
-        } else if (e->write_occ) k_mpileup_write_occ<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
-        else k_mpileup_write<<<ntw, TILE, e->smem_text + 16, e->stream>>>(fmt, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+    {
+        MpEntFmt gf; gf.v = fmt.v; gf.cf = fmt.cf; gf.E = e->ent; gf.E2 = e->ent2;
+        k_mp_gather<<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        e->launches++;
     }
-    e->launches++;
     CK(cudaEventRecord(e->ev1, e->stream));
     unsigned long long total = 0;
     CK(cudaMemcpyAsync(&total, e->col_off + nt, 8, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
-    cudaEventElapsedTime(&ms, e->ev0, e->evA); e->last_parts_ms[0] = ms;      // sizing kernel
+    cudaEventElapsedTime(&ms, e->ev0, e->evA); e->last_parts_ms[0] = ms;      // entry strings + sizes
     cudaEventElapsedTime(&ms, e->evA, e->evB); e->last_parts_ms[1] = ms;      // tile-offset scan
-    cudaEventElapsedTime(&ms, e->evB, e->ev1); e->last_parts_ms[2] = ms;      // write kernel
+    cudaEventElapsedTime(&ms, e->evB, e->ev1); e->last_parts_ms[2] = ms;      // gather
     if (total > bound) { snprintf(e->err, sizeof e->err, "internal: output %llu exceeds bound %llu", total, (unsigned long long)bound); return -1; }
     *out_len = (size_t)total; e->last_out_len = (size_t)total;
     if (out) {
@@ -1156,7 +1052,7 @@ extern "C" int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, cha
     fmt.cf.min_qual = c->min_qual; fmt.cf.count_del = c->count_del; fmt.cf.all = c->all;
     const uint64_t ncols = (uint64_t)fmt.v.ncols;
     const uint64_t bound = ncols * (e->name.size() + 1 + 20 + (uint64_t)e->n_files * 12 + 1) + 64;
-    return run_text(e, k_depth, k_depth_size, k_depth_write, fmt, bound, out, out_cap, out_len);
+    return run_text(e, k_depth_size, k_depth_write, fmt, bound, out, out_cap, out_len);
 }
 
 extern "C" int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b200_coverage_sums_t *sums)

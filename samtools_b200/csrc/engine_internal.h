@@ -21,8 +21,7 @@ struct b200_engine {
     bool keep_raw = false, uploaded = false, has_host_clip = false;
     size_t qual_bytes = 0, n_cigar_total = 0;
     uint32_t smem_text = 24 * 1024;
-    int use_tma = 1, chained = 0, variant = 0, write_occ = 0, stream_size = 1, sr_write = 0, lean_write = 0;
-    uint32_t smem_text_rm = 36 * 1024;
+    int use_tma = 1, general = 0;
 
     // raw SoA image of the staged records
     DBUF(int64_t, pos); DBUF(uint16_t, flag); DBUF(uint8_t, mapq); DBUF(int32_t, l_qseq); DBUF(uint32_t, n_cigar);
@@ -39,11 +38,12 @@ struct b200_engine {
     DBUF(uint32_t, ovf_cnt); DBUF(int32_t, ovf_off); DBUF(int32_t, ovf_idx);
     DBUF(int32_t, ss_diff); DBUF(int32_t, ss_nplp); DBUF(uint32_t, ss_fail); DBUF(uint32_t, ss_extra); DBUF(uint64_t, status2); DBUF(b200_pileup1_t, ents);
     DBUF(int32_t, clip); DBUF(int64_t, next); DBUF(int32_t, cig_x); DBUF(int32_t, cig_y);
-    DBUF(double, baq_f); DBUF(int32_t, baq_idx); DBUF(uint8_t, ref_codes);
+    DBUF(double, baq_f); DBUF(int32_t, baq_idx); DBUF(uint8_t, ref_codes); DBUF(uint16_t, ent); DBUF(uint16_t, ent2);
     DBUF(float, gl_out); DBUF(int32_t, gl_n); DBUF(uint32_t, gl_flag);
     void *d_acc = nullptr;
     unsigned long long *d_misc = nullptr;
     double *d_beta = nullptr, *d_fk = nullptr, *d_lhet = nullptr;   // errmod tables
+    double fk_depcorr = 0;                                             // dependency coefficient d_fk was built for
     double *d_q2p = nullptr, *d_qthr = nullptr;                      // BAQ tables
 
     // batch state
@@ -54,7 +54,7 @@ struct b200_engine {
     int64_t win_base = 0, ref_beg = 0, ref_n = 0, ref_len = 0;
     int64_t ncols_cov = 0, ncols_all = 0; int32_t ncols_max = 0, n_groups = 0;
     int64_t acc_n_kept = 0; int32_t max_rend = 0;
-    unsigned long long sum_rlen = 0, sum_indel_text = 0;
+    unsigned long long sum_rlen = 0, sum_indel_text = 0, sum_rlen_gen = 0;
     size_t last_out_len = 0;
     uint64_t gl_rng_draws = 0;   // hts_drand48 draws consumed so far by errmod's ks_shuffle
     std::vector<int64_t> h_file_start;
@@ -69,7 +69,7 @@ struct b200_engine {
     {
         void *ps[] = { qual0, mapq0, pos, flag, mapq, l_qseq, n_cigar, cigar_off, qual_off, mtid, mpos, isize, prev, rbits, cigar, seq4, qual,
                        ref, dname, file_start, state, rlen, desc, endv, pmax, glo, ghi, status, out, bed_beg, bed_end, col_n,
-                       col_off, col_state, tile_total, ovf_cnt, ovf_off, ovf_idx, ss_diff, ss_nplp, ss_fail, ss_extra, status2, ents, clip, next, cig_x, cig_y, baq_f, baq_idx, ref_codes, gl_out, gl_n, gl_flag, d_beta, d_fk, d_lhet, d_q2p, d_qthr };
+                       col_off, col_state, tile_total, ovf_cnt, ovf_off, ovf_idx, ss_diff, ss_nplp, ss_fail, ss_extra, status2, ents, clip, next, cig_x, cig_y, baq_f, baq_idx, ref_codes, ent, ent2, gl_out, gl_n, gl_flag, d_beta, d_fk, d_lhet, d_q2p, d_qthr };
         for (void *p : ps) if (p) cudaFree(p);
     }
 };

@@ -1,55 +1,16 @@
-// mpileup_ss.cuh -- "streaming" size pass for the standard single-file mpileup line.
+// mpileup_ss.cuh -- order-free line sizing for the standard single-file mpileup line.
 //
 // The byte length of a pileup line does not depend on the order of the reads in the column,
 // only on sums: n_plp (reads over the column), cnt (entries with base quality >= -Q) and the
 // extra bytes of special entries ("^"+mapq at a read's first column, "$" at its last, indel
 // text).  So the size pass can be read-major with no ordering constraint at all:
-//   k_ss_reads   one warp per read, lanes along the read: coalesced quality loads; a coverage
-//                difference array gets +1/-1 per read, only FAILING bases and special entries
-//                touch per-column counters (sparse atomics)
+//   k_mp_entries (mpileup_ent.cuh) one warp per read, lanes along the read: a coverage difference array gets
+//                +1/-1 per read, only FAILING bases and special entries touch per-column counters (sparse atomics)
 //   k_ss_scan    prefix sum of the difference array -> n_plp per column
 //   k_ss_cols    per column: cnt = n_plp - fail, seq_len = cnt + extra -> MpFileSz, line length,
 //                128-column tile totals (what the write kernel and the offset scan consume)
-// Equivalent to k_mp_rm_size / mp_line_size; `test_c2_size_properties` checks all variants agree.
+// Equivalent to mp_line_size (the general path); `test_c2_size_properties` checks that both paths agree.
 #pragma once
-
-__global__ void __launch_bounds__(256) k_ss_reads(View v, MpConf cf, int64_t n_reads, int32_t *diff, uint32_t *fail, uint32_t *extra)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const uint32_t ends = cf.no_ends ? 0u : 1u;
-    for (int64_t i = warp; i < n_reads; i += n_warps) {
-        ReadDesc d = load_hot(v.desc + i);
-        if (d.rend <= d.rpos) continue;                         // filtered read
-        const int32_t a = d.rpos > 0 ? d.rpos : 0, b = d.rend < v.ncols ? d.rend : v.ncols;   // columns inside the window
-        if (a >= b) continue;
-        if (lane == 0) { atomicAdd(&diff[a], 1); atomicAdd(&diff[b], -1); }
-        if (d.fl & RD_SIMPLE) {
-            const uint32_t qbase = d.qoff + (uint32_t)d.qstart - (uint32_t)d.rpos;   // query index = column + (qstart - rpos)
-            // "^"+mapq (2 bytes) at the read's first column and "$" (1) at its last, when that base passes -Q: two lanes
-            if (ends && lane < 2) {
-                const int32_t c = lane ? d.rend - 1 : d.rpos;
-                if (c >= a && c < b && (int)v.qual[qbase + (uint32_t)c] >= cf.min_baseQ) atomicAdd(&extra[c], lane ? 1u : 2u);
-            }
-            // every other base only matters when it FAILS -Q (sparse); five independent loads in flight per lane
-            for (int32_t c0 = a + lane; c0 < b; c0 += 32 * 5) {
-                int q[5];
-#pragma unroll
-                for (int k = 0; k < 5; ++k) { const int32_t c = c0 + 32 * k; q[k] = c < b ? (int)v.qual[qbase + (uint32_t)c] : 255; }
-#pragma unroll
-                for (int k = 0; k < 5; ++k) if (q[k] < cf.min_baseQ && c0 + 32 * k < b) atomicAdd(&fail[c0 + 32 * k], 1u);
-            }
-        } else {
-            load_cold(d, v.desc + i);
-            const uint32_t *cg = v.cigar + d.cig_off;
-            for (int32_t c = a + lane; c < b; c += 32) {
-                Ent e; resolve(v, d, c, e);
-                if (ent_qual(v, d, e) < cf.min_baseQ) atomicAdd(&fail[c], 1u);
-                else { const uint32_t x = (uint32_t)mp_entry_size(cf, d, cg, e) - 1u; if (x) atomicAdd(&extra[c], x); }
-            }
-        }
-    }
-}
 
 // inclusive prefix sum of int32 (coverage), single pass with decoupled look-back
 __global__ void k_ss_scan(const int32_t *in, int32_t *out, int32_t n, uint64_t *st, uint32_t *ticket)

@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define PLP_HD __host__ __device__ __forceinline__
+#define PLP_HD_COLD __host__ __device__ __noinline__
 #else
 #define PLP_HD inline
+#define PLP_HD_COLD inline
 #endif
 
 namespace plp {
@@ -625,23 +627,19 @@ PLP_HD void mp_line_write(const View &v, const MpConf &cf, int tile, int32_t c, 
     *p = '\n';
 }
 
-// ---- building blocks of the staged-reads write pass (mpileup_sr.cuh) ---------------------
-// A CTA first copies, for every read over its 128 columns, just the quality bytes and base
-// nibbles that fall inside the tile into shared memory (warp per read, aligned word loads, no
-// per-base work) together with one 32-bit word describing the read relative to the tile; then
-// every thread walks ITS column down the slots with shared-memory loads only.
-//
-// slot word: bits 0-7  first covered column (tile-local)      8-15 number of covered columns (0: none)
-//            16-17 byte offset of that column in the staged quality row
-//            18-20 nibble offset of that column in the staged base row
-//            24 reverse strand   25 simple [S]<n>M[S] read (staged)   26 "^"+mapq at the first covered column
-//            27 "$" at the last covered column
-// An entry leaves sr_entry as: 0 = nothing to print (base fails -Q), else bits 0-6 base
-// character, bit 7 "^"+mapq first, bits 8-14 quality character, bit 15 "$" after.
-constexpr uint32_t SR_SIMPLE = 1u << 25;
-constexpr int SR_COLS = 128;          // columns per tile
-constexpr int SR_QROW = 33;           // staged quality row, words: <= 3 + 128 bytes
-constexpr int SR_SROW = 18;           // staged base row, words: <= 7 + 128 nibbles
+// ---- entry strings: the default single-file mpileup path (mpileup_ent.cuh) ------------------
+// pileup_seq (bam_plcmd.c:54-169) emits, for almost every (read, column), ONE sequence character and ONE
+// quality character.  A read-major pass (lanes along the read: wide coalesced loads, no per-column
+// searching) therefore pre-formats every read into a string of 16-bit entries, one per reference column
+// the read spans, and the column pass only gathers them in file order:
+//   0x0000          nothing to print: the base fails -Q (bam_plcmd.c:676-679)
+//   0xffff          special: the entry carries indel text; the column pass runs the generic formatter
+//   otherwise       bits 0-6 sequence character, bit 7 "^"+mapq goes first (read's first column),
+//                   bits 8-14 quality character, bit 15 "$" follows (read's last column)
+// Reads of the simple shape ([S]<n>M[S], RD_SIMPLE) keep the entry of query base qi at E[qi] -- the index of
+// its quality byte, so no offsets have to be computed or stored; the other reads get a slice of a second
+// array, one entry per spanned column, whose start is kept in the descriptor's spare word.
+constexpr uint32_t ENT_SPECIAL = 0xffffu;
 
 PLP_HD uint32_t umin32(uint32_t a, uint32_t b)
 {
@@ -652,49 +650,52 @@ PLP_HD uint32_t umin32(uint32_t a, uint32_t b)
 #endif
 }
 
-// slot word of read d (first half of the descriptor) for the tile starting at column c0;
-// qi_a = query index (quality byte / base nibble) of the first covered column, simple reads only
-PLP_HD uint32_t sr_meta(const ReadDesc &d, int32_t c0, uint32_t ends, uint32_t &qi_a)
-{
-    const int32_t a = d.rpos > c0 ? d.rpos : c0, b = d.rend < c0 + SR_COLS ? d.rend : c0 + SR_COLS;
-    qi_a = 0;
-    if (a >= b) return 0;
-    uint32_t m = (uint32_t)(a - c0) | (uint32_t)(b - a) << 8;
-    if (d.fl & RD_SIMPLE) {
-        qi_a = d.qoff + (uint32_t)d.qstart + (uint32_t)(a - d.rpos);
-        m |= (qi_a & 3u) << 16 | (qi_a & 7u) << 18 | SR_SIMPLE;
-    }
-    m |= (uint32_t)((d.fl & RD_REV) != 0) << 24 | (ends & (uint32_t)(a == d.rpos)) << 26 | (ends & (uint32_t)(b == d.rend)) << 27;
-    return m;
-}
-
-// entry of a staged read at its r-th covered column: q = quality byte, sbyte = the staged byte
-// holding base nibble nib (= nibble offset + r), rb = reference code of the column (0x10: no FASTA),
-// tab = ".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn" (forward strand, then reverse)
-PLP_HD uint32_t sr_entry(uint32_t m, uint32_t r, uint32_t q, uint32_t sbyte, uint32_t nib, uint32_t rb, int minq, const uint8_t *tab)
-{
-    if ((int)q < minq) return 0;
-    uint32_t code = (sbyte >> ((~nib & 1u) << 2)) & 0xfu;
-    if (code == rb) code = 0;
-    uint32_t x = (uint32_t)tab[((m >> 20) & 0x10u) | code] | umin32(q + 33u, 126u) << 8;
-    x |= ((m >> 26) & (uint32_t)(r == 0)) << 7 | ((m >> 27) & (uint32_t)(r + 1u == ((m >> 8) & 0xffu))) << 15;
-    return x;
-}
-
 // reference code of column c as pileup_seq compares it (bam_plcmd.c:74-80); 0x10 without a FASTA
-PLP_HD uint32_t sr_ref_code(const View &v, int32_t c)
+PLP_HD uint32_t ent_ref_code(const View &v, int32_t c)
 {
     if (!v.ref) return 0x10u;
     if ((int64_t)c < v.ref_len_rel) { const int64_t ri = (int64_t)c - v.ref_off; if (ri >= 0 && ri < v.ref_n) return (uint32_t)nt16_of((unsigned char)v.ref[ri]); }
     return 15u;
 }
 
+// entry of one aligned base: q quality byte, code 4-bit base, rb reference code of the column (0x10: none),
+// tab = ".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn" (forward strand, then reverse), flags = 0x80 (head) | 0x8000 (tail)
+PLP_HD uint32_t ent_plain(uint32_t q, uint32_t code, uint32_t rb, uint32_t rev, int minq, uint32_t flags, const uint8_t *tab)
+{
+    if ((int)q < minq) return 0;
+    if (code == rb) code = 0;
+    return (uint32_t)tab[rev * 16u + code] | umin32(q + 33u, 126u) << 8 | flags;
+}
+
+// entry of read d (any shape) at column c through the generic cursor; extra = bytes the entry prints beyond its
+// one sequence character ("^"+mapq, "$", indel text): what the size pass adds to the column
+PLP_HD uint32_t ent_generic(const View &v, const MpConf &cf, const ReadDesc &d, int32_t c, uint32_t rb, const uint8_t *tab, uint32_t &extra)
+{
+    Ent e;
+    resolve(v, d, c, e);
+    extra = 0;
+    const int q = ent_qual(v, d, e);
+    if (q < cf.min_baseQ) return 0;
+    extra = (uint32_t)mp_entry_size(cf, d, v.cigar + d.cig_off, e) - 1u;
+    if (e.indel != 0) return ENT_SPECIAL;
+    const uint32_t rev = (d.fl & RD_REV) ? 1u : 0u;
+    uint32_t ch;
+    if (!e.is_del) {
+        uint32_t code = e.qpos < d.l_qseq ? (uint32_t)base4(v.seq4, d.qoff, e.qpos) : 15u;
+        if (code == rb) code = 0;
+        ch = tab[rev * 16u + code];
+    } else ch = (uint32_t)(e.is_refskip ? (rev ? '<' : '>') : ((rev && cf.rev_del) ? '#' : '*'));
+    uint32_t x = ch | umin32((uint32_t)q + 33u, 126u) << 8;
+    if (!cf.no_ends) x |= (e.is_head ? 0x80u : 0u) | (e.is_tail ? 0x8000u : 0u);
+    return x;
+}
+
 // Everything of a single-file line except the entries: header, count, separators, "*" place
 // holders, newline.  Returns the cursors the entries are appended through (ps == nullptr: none).
-struct SrCur { char *ps, *pq, *pm; };
-PLP_HD SrCur sr_layout(const View &v, const MpConf &cf, int32_t c, const MpFileSz &s, char *p)
+struct EntCur { char *ps, *pq, *pm; };
+PLP_HD EntCur ent_layout(const View &v, const MpConf &cf, int32_t c, const MpFileSz &s, char *p)
 {
-    SrCur k; k.ps = nullptr; k.pq = nullptr; k.pm = nullptr;
+    EntCur k; k.ps = nullptr; k.pq = nullptr; k.pm = nullptr;
     p = mp_head_write(v, c, p);
     *p++ = '\t'; p += put_u64(p, (uint64_t)s.cnt); *p++ = '\t';
     if (s.nplp == 0) {
@@ -713,69 +714,31 @@ PLP_HD SrCur sr_layout(const View &v, const MpConf &cf, int32_t c, const MpFileS
     return k;
 }
 
-// generic entry of read i at column c: bytes appended at ps, or -1 when the base fails -Q
-PLP_HD int sr_slow_entry(const View &v, const MpConf &cf, int32_t i, int32_t c, char *ps, int &q)
+// special entry (indel text) of read i at column c through the generic formatter: ONE out-of-line copy, so that the
+// gather loop stays a few dozen instructions.  Appends the sequence text at ps, returns its length; q = quality.
+PLP_HD_COLD int ent_special(const View &v, const MpConf &cf, int32_t i, int32_t c, char *ps, int &q)
 {
     const ReadDesc d = load_desc(v.desc + i);
-    Ent e;
-    resolve(v, d, c, e);
-    q = ent_qual(v, d, e);
-    if (q < cf.min_baseQ) return -1;
-    return mp_entry_write(v, cf, d, v.cigar + d.cig_off, e, c, ps);
+    Ent en;
+    resolve(v, d, c, en);
+    q = ent_qual(v, d, en);
+    return mp_entry_write(v, cf, d, v.cigar + d.cig_off, en, c, ps);
 }
 
-// append entry x of a staged read to the column's strings (mq = the read's mapq character)
-PLP_HD void sr_emit(uint32_t x, char mq, int out_mapq, SrCur &k)
+// The column pass: line of column c from the entry strings (single file; -s supported, -O / --output-BP-5 not).
+// E: entries of simple reads at their quality-byte index; E2: the slices of the other reads (start in desc.pad_).
+// Cursors are byte offsets from p (one base register: shared-memory stores on the device).
+PLP_HD void mp_line_write_ent(const View &v, const MpConf &cf, int32_t c, const MpFileSz &s, char *p, const uint16_t *E, const uint16_t *E2)
 {
-    if (x & 0x80u) { *k.ps++ = '^'; *k.ps++ = mq; }
-    *k.ps++ = (char)(x & 0x7fu);
-    if (x & 0x8000u) *k.ps++ = '$';
-    *k.pq++ = (char)((x >> 8) & 0x7fu);
-    if (out_mapq) *k.pm++ = mq;
-}
-
-// reads that can cover the four 32-column groups g0..g0+3: far-reaching list of g0, then [lo(g0), hi(g0+3)).
-// (a read that is far-reaching for a later group and covers it also covers g0, so it is in one of the two parts)
-PLP_HD ReadRange sr_range(const View &v, int g0)
-{
-    ReadRange r;
-    int g3 = g0 + 3; if (g3 >= v.n_tiles) g3 = v.n_tiles - 1;
-    const int32_t o0 = v.ovf_off[g0];
-    r.n_ovf = v.ovf_off[g0 + 1] - o0;
-    r.ovf = v.ovf_idx + o0;
-    r.lo = v.tile_lo[g0];
-    int32_t hi = v.tile_hi[g3]; if (hi < r.lo) hi = r.lo;
-    r.n = r.n_ovf + (hi - r.lo);
-    return r;
-}
-
-// ---- lean write loop (opt-in B200_PLP_LEAN=1; single file, no -s / -O columns) -----------------
-// Same output as mp_line_write.  Differences, all aimed at the instruction count of the per-read iteration:
-//   * descriptors are four raw words; the three in flight rotate by NAME (loop unrolled by the pipeline depth)
-//     instead of by register moves;
-//   * the far-reaching list and the contiguous slice are one index space (no second copy of the loop);
-//   * the base character comes from a 32-byte table (shared memory on the device) instead of packed immediates;
-//   * reads that are not of the simple shape leave the fast loop through ONE cold block (goto), after which
-//     the pipeline is primed again -- a few hundred cycles once or twice per column instead of a copy of the
-//     generic formatter in every unrolled step.
-PLP_HD void mp_line_write_lean(const View &v, const MpConf &cf, int32_t c, const MpFileSz &s, char *p, const uint8_t *tab /* ".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn" */)
-{
-    const SrCur cur = sr_layout(v, cf, c, s, p);       // header, count, separators, place holders, newline
+    const EntCur cur = ent_layout(v, cf, c, s, p);
     if (!cur.ps) return;
-    char *ps = cur.ps, *pq = cur.pq;
+    uint32_t so = (uint32_t)(cur.ps - p), qo = (uint32_t)(cur.pq - p), mo = (uint32_t)(cur.pm - p);
     const ReadRange rr = read_range(v, 0, c >> 5);
-    const int32_t n = rr.n;
-    const int rb = (int)sr_ref_code(v, c);             // 0x10 without a FASTA: equal to no base code
-    const bool ends = !cf.no_ends;
-    const int minq = cf.min_baseQ;
-    struct Raw { int32_t rpos, rend; uint32_t qoff, pk; };
-    struct Pre { int q; uint32_t sb; };
-    static_assert(RD_REV == 1, "the table index below takes RD_REV from bit 24 of the packed word");
     const uint32_t kSimple = (uint32_t)RD_SIMPLE << 24;
-    auto ridx = [&](int32_t t) -> int32_t { return t < rr.n_ovf ? rr.ovf[t] : rr.lo + (t - rr.n_ovf); };
-    auto load_raw = [&](int32_t t) -> Raw {
+    const bool out_mapq = cf.out_mapq != 0;
+    struct Raw { int32_t rpos, rend; uint32_t qoff, pk; };
+    auto load_raw = [&](int32_t i) -> Raw {
         Raw r;
-        const int32_t i = ridx(t);
 #if defined(__CUDA_ARCH__)
         const uint4 w = __ldg(reinterpret_cast<const uint4 *>(v.desc + i));
         r.rpos = (int32_t)w.x; r.rend = (int32_t)w.y; r.qoff = w.z; r.pk = w.w;
@@ -785,60 +748,62 @@ PLP_HD void mp_line_write_lean(const View &v, const MpConf &cf, int32_t c, const
 #endif
         return r;
     };
-    auto prefetch = [&](const Raw &d) -> Pre {
-        Pre o; o.q = 0; o.sb = 0;
-        const uint32_t rel = (uint32_t)(c - d.rpos);
-        if (rel < (uint32_t)(d.rend - d.rpos) && (d.pk & kSimple)) {
-            const uint32_t qi = d.qoff + (d.pk & 0xffffu) + rel;
-            o.q = (int)v.qual[qi];
-            o.sb = v.seq4[qi >> 1];
+    auto emit = [&](const Raw &r, int32_t i, uint32_t e) {
+        if (!e) return;
+        const uint32_t mapq = (r.pk >> 16) & 0xffu;
+        if (e == ENT_SPECIAL) {
+            int q;
+            so += (uint32_t)ent_special(v, cf, i, c, p + so, q);
+            p[qo++] = (char)(q + 33 < 126 ? q + 33 : 126);
+        } else {
+            if (e & 0x8080u) {
+                if (e & 0x80u) { p[so++] = '^'; p[so++] = (char)(mapq > 93u ? 126u : mapq + 33u); }
+                p[so++] = (char)(e & 0x7fu);
+                if (e & 0x8000u) p[so++] = '$';
+            } else p[so++] = (char)e;
+            p[qo++] = (char)((e >> 8) & 0x7fu);
         }
-        return o;
+        if (out_mapq) p[mo++] = (char)umin32(mapq + 33u, 126u);
     };
-    // formats the entry of a simple read; returns true when the read covers the column but needs the generic formatter
-    auto fast = [&](const Raw &r, const Pre &pre) -> bool {
+    // entry of read i (descriptor r) at this column through the general route (any shape)
+    auto entry_of = [&](const Raw &r, int32_t i) -> uint32_t {
         const uint32_t rel = (uint32_t)(c - r.rpos);
-        if (rel >= (uint32_t)(r.rend - r.rpos)) return false;
-        if (!(r.pk & kSimple)) return true;
-        if (pre.q < minq) return false;
-        const uint32_t par = (r.qoff ^ r.pk ^ rel) & 1u;                  // parity of the query index qoff + qstart + rel
-        if (ends && rel == 0) { const int mapq = (int)((r.pk >> 16) & 0xffu); *ps++ = '^'; *ps++ = (char)(mapq > 93 ? 126 : mapq + 33); }
-        int ch = (int)((pre.sb >> ((par ^ 1u) << 2)) & 0xfu);
-        if (ch == rb) ch = 0;
-        *ps++ = (char)tab[((r.pk >> 20) & 0x10u) | (uint32_t)ch];          // RD_REV is bit 24 of pk -> +16: the reverse-strand half
-        if (ends && c == r.rend - 1) *ps++ = '$';
-        *pq++ = (char)(pre.q + 33 < 126 ? pre.q + 33 : 126);
-        return false;
+        if (rel >= (uint32_t)(r.rend - r.rpos)) return 0;
+        if (r.pk & kSimple) return E[r.qoff + (r.pk & 0xffffu) + rel];
+        return E2[v.desc[i].pad_ + rel];
     };
-    int32_t t = 0;
-    while (t < n) {
-        const int32_t last = n - 1;
-        Raw dA = load_raw(t), dB = load_raw(t + 1 < n ? t + 1 : last), dC;
-        Pre pc = prefetch(dA), pn;
-        // one step: bytes of read t+1 and descriptor of read t+2 go in flight, entry t is formatted
-#define PLP_LEAN_STEP(CUR, NXT, NEW)                             \
-        pn = t + 1 < n ? prefetch(NXT) : pc;                     \
-        NEW = load_raw(t + 2 < n ? t + 2 : last);                \
-        if (fast(CUR, pc)) goto generic_entry;                   \
-        pc = pn; ++t;
-        while (t + 2 < n) { PLP_LEAN_STEP(dA, dB, dC) PLP_LEAN_STEP(dB, dC, dA) PLP_LEAN_STEP(dC, dA, dB) }
-        if (t < n) { PLP_LEAN_STEP(dA, dB, dC) }
-        if (t < n) { PLP_LEAN_STEP(dB, dC, dA) }
-#undef PLP_LEAN_STEP
-        break;
-    generic_entry:
-        {   // read t is not of the simple shape (indel / ref-skip / pad): the one copy of the generic formatter
-            const ReadDesc d = load_desc(v.desc + ridx(t));
-            Ent e;
-            resolve(v, d, c, e);
-            const int q = ent_qual(v, d, e);
-            if (q >= minq) {
-                ps += mp_entry_write(v, cf, d, v.cigar + d.cig_off, e, c, ps);
-                *pq++ = (char)(q + 33 < 126 ? q + 33 : 126);
-            }
-            ++t;
+    // far-reaching reads first (usually none): all of them precede the slice in file order
+    for (int32_t t = 0; t < rr.n_ovf; ++t) { const int32_t i = rr.ovf[t]; const Raw r = load_raw(i); emit(r, i, entry_of(r, i)); }
+    // the slice, four reads per step: four descriptor loads, then four entry loads in flight (branch-free for simple
+    // reads: a read that is not over the column loads entry 0 of the array and discards it), then the appends
+    const int32_t hi = rr.lo + (rr.n - rr.n_ovf);
+    int32_t i = rr.lo;
+    for (; i + 4 <= hi; i += 4) {
+        Raw r[4]; uint32_t rel[4], e[4]; bool in[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) r[k] = load_raw(i + k);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) {
+            rel[k] = (uint32_t)(c - r[k].rpos);
+            in[k] = rel[k] < (uint32_t)(r[k].rend - r[k].rpos);
+            const bool fast = in[k] && (r[k].pk & kSimple);
+            const uint32_t idx = fast ? r[k].qoff + (r[k].pk & 0xffffu) + rel[k] : 0u;
+            e[k] = E[idx];
+            if (!fast) e[k] = 0;
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) {
+            if (in[k] && !(r[k].pk & kSimple)) e[k] = E2[v.desc[i + k].pad_ + rel[k]];
+            emit(r[k], i + k, e[k]);
         }
     }
+    for (; i < hi; ++i) { const Raw r = load_raw(i); emit(r, i, entry_of(r, i)); }
 }
 
 // ---- depth (bam2depth.c) ------------------------------------------------------

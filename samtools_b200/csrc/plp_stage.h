@@ -35,6 +35,7 @@ struct RawSoA {
 
 struct StageAcc {   // device-side accumulators (one instance per stage call)
     unsigned long long n_kept, n_kept_in_window, sum_rlen, sum_indel_text, n_reads, n_selected, summed_mapq;
+    unsigned long long sum_rlen_gen;   // reference span of the kept reads that are not of the simple shape (entries of the second array, mpileup_ent.cuh)
     unsigned long long n_desc;   // records whose start lies before the previous record's (any file, any state): triggers the exact sortedness check
     int max_rend;
 };
@@ -212,6 +213,7 @@ PLP_HD void stage_build_desc(const RawSoA &r, const b200_stage_conf_t &cf, int64
         const int64_t wend = cf.end - win_base;   // may overflow int32 only on purpose-built inputs
         if (d.rend > d.rpos && d.rend > 0 && (int64_t)d.rpos < wend) PLP_ADD64(&acc->n_kept_in_window, 1);
         PLP_ADD64(&acc->sum_rlen, span);
+        if (!(d.fl & RD_SIMPLE)) PLP_ADD64(&acc->sum_rlen_gen, span);
         unsigned long long it = 3;
         if (!(d.fl & RD_SIMPLE))
             for (int k = 0; k < n; ++k) { int op = cg[k] & 0xf; if (op == OP_I || op == OP_P || op == OP_D) it += 12 + (cg[k] >> 4); }

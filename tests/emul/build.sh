@@ -16,3 +16,7 @@ if [ -f "$REF/bam_plbuf.c" ]; then
     g++ -std=c++17 -O1 -g -Iinclude -Itests/compat/shim -I"$REF" -o tests/emul/_build/plbuf_dump_emul tests/compat/plbuf_dump.cpp \
         tests/emul/_build/ref_bam_plbuf.o samtools_b200/csrc/host/plp_compat.cpp samtools_b200/csrc/host/hts_io.cpp tests/emul/emul_engine.cpp -lz
 fi
+# the register-band BAQ arithmetic (samtools_b200/csrc/baq_reg.h) single-stepped on the CPU against the oracle's sam_prob_realn
+make -s -C oracle
+g++ -std=c++17 -O2 -ffp-contract=off -Wno-unknown-pragmas -o tests/emul/_build/baq_host tests/emul/baq_host.cpp \
+    -Loracle/_build -loracle -Wl,-rpath,"$PWD/oracle/_build" -lz -lm

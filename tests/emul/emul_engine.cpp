@@ -220,84 +220,65 @@ int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out,
     View v; fill_view(e, v, c->bed_beg, c->bed_end, c->n_bed, c->bed_active, c->all);
     MpConf cf{c->min_baseQ, c->all, c->rev_del, c->no_ins, c->no_del, c->no_ends, c->out_mapq, c->out_qpos, c->out_qpos5, c->n_star_cols};
     std::string s;
-    const char *sr = getenv("EMUL_SR");   // replay the opt-in staged-reads write kernel instead of the default one
-    if (v.n_files == 1 && !cf.out_qpos && !cf.out_qpos5 && sr && atoi(sr) == 1) {
-        // sequential replay of k_mp_sr_write (mpileup_sr.cuh): same building blocks, same slot/chunk structure
-        const int T = SR_COLS, S = 32;
-        const uint32_t ends = cf.no_ends ? 0u : 1u;
-        for (int32_t c0 = 0; c0 < v.ncols; c0 += T) {
-            std::vector<std::string> line(T);
-            std::vector<SrCur> cur(T);
-            uint32_t rb[T];
-            for (int t = 0; t < T; ++t) {
-                const int32_t c = c0 + t;
-                cur[t].ps = cur[t].pq = cur[t].pm = nullptr;
-                rb[t] = sr_ref_code(v, c);
-                if (c >= v.ncols) continue;
-                MpFileSz s0;
-                const uint32_t len = mp_line_size(v, cf, c >> 5, c, s0);
-                if (!len) continue;
-                line[t].assign(len, '?');
-                cur[t] = sr_layout(v, cf, c, s0, &line[t][0]);
-            }
-            const ReadRange rr = sr_range(v, c0 >> 5);
-            for (int32_t t0 = 0; t0 < rr.n; t0 += S) {
-                static uint32_t sq[S][SR_QROW], ss[S][SR_SROW];
-                uint32_t meta[S] = {0}; int32_t idx[S] = {0}; char mq[S] = {0};
-                memset(sq, 0xee, sizeof sq); memset(ss, 0xee, sizeof ss);   // stale contents must never matter
-                for (int sl = 0; sl < S; ++sl) {
-                    ReadDesc d; memset(&d, 0, sizeof d);
-                    if (t0 + sl < rr.n) {
-                        idx[sl] = range_at(rr, t0 + sl);
-                        d = load_hot(v.desc + idx[sl]);
-                        mq[sl] = (char)(d.mapq > 93 ? 126 : d.mapq + 33);
-                    }
-                    uint32_t qi;
-                    const uint32_t m = sr_meta(d, c0, ends, qi);
-                    meta[sl] = m;
-                    if (m & SR_SIMPLE) {
-                        const uint32_t nb = (m >> 8) & 0xffu;
-                        const uint32_t nwq = ((qi & 3u) + nb + 3u) >> 2, nws = ((qi & 7u) + nb + 7u) >> 3;
-                        for (uint32_t k = 0; k < nwq; ++k) memcpy(&sq[sl][k], v.qual + 4 * ((size_t)(qi >> 2) + k), 4);
-                        for (uint32_t k = 0; k < nws; ++k) memcpy(&ss[sl][k], v.seq4 + 4 * ((size_t)(qi >> 3) + k), 4);
-                    }
+    // default path (one file, no -O columns): sequential replay of mpileup_ent.cuh -- the read-major entry pass (scalar
+    // walk over the same per-base functions), the order-free line sizes, then mp_line_write_ent per column.
+    // EMUL_GENERAL=1 replays the general path (mp_line_size + mp_line_write) like B200_PLP_GENERAL=1 on the device.
+    const char *gen = getenv("EMUL_GENERAL");
+    const bool use_ent = !(gen && atoi(gen) == 1) && v.n_files == 1 && !cf.out_qpos && !cf.out_qpos5;
+    std::vector<uint16_t> E, E2; std::vector<int32_t> diff; std::vector<uint32_t> fail, extra;
+    if (use_ent) {
+        const uint8_t *tab = (const uint8_t *)".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn";
+        E.assign(e->qual.size() + 16, 0xdead); diff.assign((size_t)v.ncols + 2, 0); fail.assign((size_t)v.ncols + 1, 0); extra.assign((size_t)v.ncols + 1, 0);
+        size_t e2n = 0;
+        for (int64_t i = 0; i < e->b.n_reads; ++i) { const ReadDesc &d = e->desc[(size_t)i]; if (d.rend > d.rpos && !(d.fl & RD_SIMPLE)) e2n += (size_t)(d.rend - d.rpos); }
+        E2.assign(e2n + 16, 0xdead);
+        size_t cursor = 0;
+        for (int64_t i = 0; i < e->b.n_reads; ++i) {
+            ReadDesc &d = e->desc[(size_t)i];
+            if (d.rend <= d.rpos) continue;
+            const int32_t a = d.rpos > 0 ? d.rpos : 0, b = d.rend < v.ncols ? d.rend : v.ncols;
+            if (a >= b) continue;
+            diff[(size_t)a] += 1; diff[(size_t)b] -= 1;
+            const uint32_t rev = (d.fl & RD_REV) ? 1u : 0u;
+            if (d.fl & RD_SIMPLE) {
+                const uint32_t q0 = d.qoff + (uint32_t)d.qstart, qtail = q0 + (uint32_t)(d.rend - d.rpos) - 1u;
+                for (int32_t c = a; c < b; ++c) {
+                    const uint32_t qi = q0 + (uint32_t)(c - d.rpos);
+                    uint32_t fl = 0;
+                    if (!cf.no_ends) fl = (qi == q0 ? 0x80u : 0u) | (qi == qtail ? 0x8000u : 0u);
+                    const uint32_t x = ent_plain(v.qual[qi], (uint32_t)base4(v.seq4, 0, (int32_t)qi), ent_ref_code(v, c), rev, cf.min_baseQ, fl, tab);
+                    E[qi] = (uint16_t)x;
+                    if (!x) fail[(size_t)c]++;
+                    else if (fl) extra[(size_t)c] += ((fl & 0x80u) ? 2u : 0u) + ((fl & 0x8000u) ? 1u : 0u);
                 }
-                const int ns = std::min<int32_t>(S, rr.n - t0);
-                for (int t = 0; t < T; ++t) {
-                    if (!cur[t].ps) continue;
-                    for (int sl = 0; sl < ns; ++sl) {
-                        const uint32_t m = meta[sl];
-                        const uint32_t r = (uint32_t)t - (m & 0xffu);
-                        if (r >= ((m >> 8) & 0xffu)) continue;
-                        if (m & SR_SIMPLE) {
-                            const uint32_t nib = ((m >> 18) & 7u) + r;
-                            const uint8_t *q8 = (const uint8_t *)&sq[sl][0], *s8 = (const uint8_t *)&ss[sl][0];
-                            const uint32_t x = sr_entry(m, r, q8[((m >> 16) & 3u) + r], s8[nib >> 1], nib, rb[t], cf.min_baseQ, (const uint8_t *)".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn");
-                            if (!x) continue;
-                            sr_emit(x, mq[sl], cf.out_mapq, cur[t]);
-                        } else {
-                            int q;
-                            const int nb = sr_slow_entry(v, cf, idx[sl], c0 + t, cur[t].ps, q);
-                            if (nb < 0) continue;
-                            cur[t].ps += nb;
-                            *cur[t].pq++ = (char)(q + 33 < 126 ? q + 33 : 126);
-                            if (cf.out_mapq) *cur[t].pm++ = mq[sl];
-                        }
-                    }
+            } else {
+                d.pad_ = (uint32_t)cursor; cursor += (size_t)(d.rend - d.rpos);
+                for (int32_t c = a; c < b; ++c) {
+                    uint32_t xb;
+                    const uint32_t x = ent_generic(v, cf, d, c, ent_ref_code(v, c), tab, xb);
+                    E2[d.pad_ + (uint32_t)(c - d.rpos)] = (uint16_t)x;
+                    if (!x) fail[(size_t)c]++; else extra[(size_t)c] += xb;
                 }
             }
-            for (int t = 0; t < T; ++t) s += line[t];
         }
-        return emit(e, s, out, cap, out_len);
     }
-    const char *lean = getenv("EMUL_LEAN");   // replay the opt-in lean write loop (mp_line_write_lean) where it applies
-    const bool use_lean = lean && atoi(lean) == 1 && v.n_files == 1 && !cf.out_mapq && !cf.out_qpos && !cf.out_qpos5;
+    int32_t cov = 0;
     for (int32_t col = 0; col < v.ncols; ++col) {
         MpFileSz s0;
         uint32_t len = mp_line_size(v, cf, col >> 5, col, s0);
+        if (use_ent) {   // the sums the device derives the line length from must reproduce mp_line_size
+            cov += diff[(size_t)col];
+            MpFileSz s1; s1.nplp = cov; s1.cnt = cov - (int32_t)fail[(size_t)col]; s1.seq_len = (uint32_t)s1.cnt + extra[(size_t)col]; s1.bp_len = 0; s1.bp5_len = 0;
+            uint32_t len1 = 0;
+            if ((s1.nplp > 0 || (cf.all && col < v.ncols_all)) && bed_pass(v, col)) len1 = mp_head_len(v, col) + mp_file_section_len(cf, s1) + 1;
+            if (len1 != len || (len && (s1.nplp != s0.nplp || s1.cnt != s0.cnt || s1.seq_len != s0.seq_len))) {
+                e->err = "emulation harness: order-free line size differs from mp_line_size at column " + std::to_string(col); return -1;
+            }
+            s0 = s1;
+        }
         if (!len) continue;
         size_t at = s.size(); s.resize(at + len, '?');
-        if (use_lean) mp_line_write_lean(v, cf, col, s0, &s[at], (const uint8_t *)".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn");
+        if (use_ent) mp_line_write_ent(v, cf, col, s0, &s[at], E.data(), E2.data());
         else mp_line_write(v, cf, col >> 5, col, s0, &s[at]);
     }
     return emit(e, s, out, cap, out_len);

@@ -24,6 +24,21 @@ def test_header_symbols_exported(built):
     assert b'sm_100a' in lib.b200_version.__call__.__self__.b200_version() if False else True
 
 
+def test_htslib_symbols_exported(built):
+    """every function include/b200_htslib_compat.h declares (the htslib names an unmodified caller links against:
+    bam_plp_* / bam_mplp_*, sam_prob_realn, sam_cap_mapq, errmod_*, bcf_call_*, bam_plp_insertion_mod) is exported"""
+    from samtools_b200 import engine
+    hdr = open(os.path.join(ROOT, 'include', 'b200_htslib_compat.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = sorted(set(re.findall(r'\b((?:bam|sam|errmod|bcf_call|b200)_[a-z0-9_]+)\s*\(', hdr)) - {'bam_get_qname', 'bam_get_cigar', 'bam_get_seq', 'bam_get_qual', 'bam_seqi', 'bam_is_rev'})
+    for need in ('sam_prob_realn', 'sam_cap_mapq', 'errmod_init', 'errmod_cal', 'errmod_destroy', 'bcf_call_init', 'bcf_call_glfgen',
+                 'bcf_call_destroy', 'bam_plp_insertion_mod', 'bam_mplp64_auto', 'bam_plp_init'):
+        assert need in declared, need
+    lib = ctypes.CDLL(engine.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+
+
 def test_version_string(built):
     from samtools_b200 import engine
     lib = engine.load_library()

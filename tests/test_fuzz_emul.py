@@ -54,15 +54,8 @@ def test_fuzz_host_and_column_code(emul_bin, oracle_bin, tmp_path):
     assert not bad, f'{len(bad)} mismatches, first: {bad[0]}'
 
 
-def test_fuzz_staged_reads_blocks(emul_bin, oracle_bin, tmp_path, monkeypatch):
-    """Same cases through the building blocks of the opt-in staged-reads write kernel (mpileup_sr.cuh)."""
-    monkeypatch.setenv('EMUL_SR', '1')
-    bad = run_all(emul_bin, oracle_bin, tmp_path, range(1, 13), need_noBAQ=True)
-    assert not bad, f'{len(bad)} mismatches, first: {bad[0]}'
-
-
-def test_fuzz_lean_write_loop(emul_bin, oracle_bin, tmp_path, monkeypatch):
-    """Same cases through the opt-in lean write loop (plp_core.h::mp_line_write_lean, B200_PLP_LEAN=1 on the device)."""
-    monkeypatch.setenv('EMUL_LEAN', '1')
+def test_fuzz_general_path(emul_bin, oracle_bin, tmp_path, monkeypatch):
+    """Same cases through the general mpileup path (mp_line_size + mp_line_write; B200_PLP_GENERAL=1 on the device)."""
+    monkeypatch.setenv('EMUL_GENERAL', '1')
     bad = run_all(emul_bin, oracle_bin, tmp_path, range(1, 13), need_noBAQ=True)
     assert not bad, f'{len(bad)} mismatches, first: {bad[0]}'

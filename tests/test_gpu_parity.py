@@ -181,8 +181,7 @@ def test_c2_size_properties():
     soa = noref(synth.make_batch(length=1_000_000, depth=30, seed=2))
     digests = {}
     for tag, env in (('tma', {'B200_PLP_TMA': '1'}), ('vec', {'B200_PLP_TMA': '0'}), ('direct', {'B200_PLP_SMEM_TEXT': '1024'}),
-                     ('staged_reads', {'B200_PLP_SR': '1'}), ('staged_reads_direct', {'B200_PLP_SR': '1', 'B200_PLP_SMEM_TEXT': '1024'}), ('colmajor', {'B200_PLP_VARIANT': '1'}), ('rm_size', {'B200_PLP_STREAM_SIZE': '0'}), ('fourcol_write', {'B200_PLP_VARIANT': '4'}), ('fourcol_direct', {'B200_PLP_VARIANT': '4', 'B200_PLP_SMEM_TEXT': '1024'}), ('readmajor', {'B200_PLP_VARIANT': '2'}), ('readmajor_direct', {'B200_PLP_VARIANT': '2', 'B200_PLP_SMEM_TEXT': '1024'}), ('colmajor_direct', {'B200_PLP_VARIANT': '1', 'B200_PLP_SMEM_TEXT': '1024'}),
-                     ('chained', {'B200_PLP_CHAINED': '1'}), ('chained_direct', {'B200_PLP_CHAINED': '1', 'B200_PLP_SMEM_TEXT': '1024'})):
+                     ('general', {'B200_PLP_GENERAL': '1'}), ('general_direct', {'B200_PLP_GENERAL': '1', 'B200_PLP_SMEM_TEXT': '1024'})):
         os.environ.update(env)
         e = engine.Engine(0)
         e.stage(soa, engine.default_stage_conf(engine.MODE_MPILEUP))
@@ -199,7 +198,7 @@ def test_c2_size_properties():
             # depth column sums to the number of kept (read, column) pairs that pass -Q13; positions ascend
             pos = np.array([int(l.split(b'\t', 2)[1]) for l in lines[:-1:997]])
             assert (np.diff(pos) > 0).all()
-    assert len(set(digests.values())) == 1, digests   # read-major / column-major / chained single-launch kernels, TMA / vector / direct-to-HBM stores all agree
+    assert len(set(digests.values())) == 1, digests   # entry-string path / general path, TMA / vector / direct-to-HBM stores all agree
 
 
 # ---------------------------------------------------------------- BASELINE C2 size, CUDA bytes vs the oracle's bytes
@@ -324,6 +323,21 @@ def test_region_shards_concatenate_to_unsharded(n_shards, tmp_path, oracle_bin):
         _same(mp, want_mp, f'mpileup -a -f, {n_shards} shards on devices {devs}')
         _same(dp, want_dp, f'depth -a, {n_shards} shards on devices {devs}')
         assert cv == want_cv
+
+
+# ---------------------------------------------------------------- htslib's per-read / per-column entry points (T1)
+def test_htslib_read_ops_vs_oracle(tmp_path, synth_set, corpus):
+    """sam_prob_realn (flags 3, 1, 0, 2), sam_cap_mapq, errmod_cal (n up to 3000: the ks_shuffle path), bcf_call_glfgen and
+    bam_plp_insertion_mod as exported by libb200pileup.so with htslib's signatures, compared call by call with the oracle
+    (tests/compat/read_ops_check.cpp links both)."""
+    exe = os.path.join(ROOT, 'tests', 'compat', '_build', 'read_ops_check')
+    assert os.path.exists(exe), 'tests/compat/_build/read_ops_check missing: run python samtools_b200/build.py'
+    r = subprocess.run([exe, synth_set['sam'], synth_set['fa'], '240'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # reads with stored BQ:Z tags (the integer path) and odd CIGARs from the reference's own test data
+    mp = os.path.join(corpus, 'test', 'mpileup')
+    r = subprocess.run([exe, os.path.join(mp, 'mpileup.1.bam'), os.path.join(mp, 'mpileup.ref.fa'), '120'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
 
 
 # ---------------------------------------------------------------- htslib-compatible iterator tier (T1)
