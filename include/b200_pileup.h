@@ -88,6 +88,9 @@ typedef struct {
 #define B200_RB_HOST_SKIP 1   /* dropped by a host-side string filter (BED -l per read, RG -G) */
 #define B200_RB_NAME_ODD  2   /* __ac_Wang_hash(__ac_X31_hash_string(qname)) & 1: which mate keeps the evidence */
 #define B200_RB_BAQ_DONE  4   /* BAQ already applied from a stored BQ:Z tag (integer path) */
+#define B200_RB_HALO      8   /* the read starts before this window and was already staged with the previous one (a driver that
+                                 cuts a reference sequence into column windows stages every read overlapping a window: the -r
+                                 rule, bam_plcmd.c:550-554,609): leave it out of the coverage read statistics (coverage.c:185-193) */
 
 /* ---- read-level configuration (what happens before a read is pushed) ---- */
 typedef enum { B200_MODE_MPILEUP = 0, B200_MODE_DEPTH = 1, B200_MODE_COVERAGE = 2 } b200_mode_t;
@@ -178,6 +181,10 @@ int b200_stage(b200_engine_t *e, const b200_batch_t *batch, const b200_stage_con
  * HBM (device-only timing); *out_len always receives the byte count. */
 int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *conf, char *out, size_t out_cap, size_t *out_len);
 int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *conf, char *out, size_t out_cap, size_t *out_len);
+/* upper bounds of what the text calls can write for the staged batch with these options (a few per cent above the real size): a
+ * caller sizes its host buffer once and gets the text in ONE call instead of asking for the length first */
+uint64_t b200_mpileup_text_bound(const b200_engine_t *e, const b200_mpileup_conf_t *conf);
+uint64_t b200_depth_text_bound(const b200_engine_t *e);
 int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *conf, b200_coverage_sums_t *sums);
 /* genotype likelihoods per covered column and file: n, qsum[4], p[25].  col_pos == NULL: compute only, results stay in
  * HBM (device-only timing, like out == NULL of the text calls); *n_cols is then the number of candidate columns */

@@ -146,11 +146,16 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         mem.put_row(1, M, I, 1. / sum);
         s_lq = sum;
     }
+    // the inputs of a row (one quality byte, one base byte, one reference code) are fetched ONE ROW AHEAD: each is a
+    // dependent, poorly cached byte load, and a row is ~1000 cycles of FP64 work to hide it behind
+    uint32_t nq = lq > 1 ? qual[1] : 0, ns = lq > 1 ? seq4[(qoff + 1u) >> 1] : 0;
+    int nr = (BW + 1 < l_ref) ? mem.ref_code(BW + 1) : 4;
     for (int i = 2; i <= lq; ++i) {
-        const int pn = i + BW - 1;                                   // window position entering at cell 14
-        win = (win >> 4) | ((uint64_t)(pn < l_ref ? mem.ref_code(pn) : 4) << (4 * (NB - 1)));
-        const int qc = plp::nt16_int_of(plp::base4(seq4, qoff, i - 1));
-        const double ql = q2pf[qual[i - 1]];
+        const uint32_t cq = nq, cs = ns; const int cr = nr;          // row i: query base i-1, window position i + 6 enters
+        if (i < lq) { nq = qual[i]; ns = seq4[(qoff + (uint32_t)i) >> 1]; nr = (i + BW < l_ref) ? mem.ref_code(i + BW) : 4; }
+        win = (win >> 4) | ((uint64_t)cr << (4 * (NB - 1)));
+        const int qc = plp::nt16_int_of((int)((cs >> ((~(qoff + (uint32_t)(i - 1)) & 1u) << 2)) & 0xfu));
+        const double ql = q2pf[cq];
         const double em_match = qc > 3 ? 1. : 1. - ql, em_mis = qc > 3 ? 1. : ql * BAQR_EM;
         const uint64_t xw = win ^ (kRep * (uint64_t)(qc & 7));
         double sum, inv;
@@ -179,12 +184,16 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         for (int j = 0; j < NB; ++j) { const double v = cell_valid(lq, j, l_ref) ? bv : 0.; M[j] = v; I[j] = v; }
     }
     // `win` holds positions lq + j - 8: exactly what backward row lq-1 compares against (position k = i - 7 + j)
+    // backward row i uses query base i and, from row lq-2 down, window position i - 7 entering at cell 0: one row ahead again
+    nq = lq > 1 ? qual[lq - 1] : 0; ns = lq > 1 ? seq4[(qoff + (uint32_t)(lq - 1)) >> 1] : 0; nr = 4;
     for (int i = lq; i >= 1; --i) {
         if (i > 1) mem.fetch(i - 1);
         if (i < lq) {
-            if (i < lq - 1) { const int pn = i - BW; win = ((win << 4) & kMask) | (uint64_t)(pn >= 0 && pn < l_ref ? mem.ref_code(pn) : 4); }
-            const int qc = plp::nt16_int_of(plp::base4(seq4, qoff, i));
-            const double ql = q2pf[qual[i]];
+            const uint32_t cq = nq, cs = ns; const int cr = nr;
+            if (i > 1) { nq = qual[i - 1]; ns = seq4[(qoff + (uint32_t)(i - 1)) >> 1]; const int pn = i - 1 - BW; nr = (pn >= 0 && pn < l_ref) ? mem.ref_code(pn) : 4; }
+            if (i < lq - 1) win = ((win << 4) & kMask) | (uint64_t)cr;
+            const int qc = plp::nt16_int_of((int)((cs >> ((~(qoff + (uint32_t)i) & 1u) << 2)) & 0xfu));
+            const double ql = q2pf[cq];
             const double em_match = qc > 3 ? 1. : 1. - ql, em_mis = qc > 3 ? 1. : ql * BAQR_EM;
             const uint64_t xw = win ^ (kRep * (uint64_t)(qc & 7));
             if (i > BW && i + BW < l_ref) {
@@ -200,14 +209,21 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
 #pragma unroll
                 for (int j = 0; j < NB; ++j) if (cell_valid(i, j, l_ref)) { M[j] *= ys; I[j] *= ys; }
             }
-        } else mem.wait(i > 1 ? 1 : 0);
+        } else {
+            // row lq: nothing to compute; prime the inputs of row lq-1 (query base lq-1 is already in nq/ns) -- its reference
+            // window is `win` as it stands, the first position to ENTER is (lq-2) - 7 for row lq-2
+            const int pn = lq - 2 - BW;
+            nr = (pn >= 0 && pn < l_ref) ? mem.ref_code(pn) : 4;
+            mem.wait(i > 1 ? 1 : 0);
+        }
         // ---- MAP of row i (cells outside the band are zero on both sides: they add 0 and never exceed the maximum)
         double sum = 0., mx = 0.; int best = -1;
 #pragma unroll
         for (int j = 0; j < NB; ++j) {
             double fM, fI; mem.get(i, j, fM, fI);
-            double z = fM * M[j]; if (z > mx) { mx = z; best = 2 * j; } sum += z;
-            z = fI * I[j];        if (z > mx) { mx = z; best = 2 * j + 1; } sum += z;
+            const double z0 = fM * M[j], z1 = fI * I[j];
+            const bool g0 = z0 > mx; mx = g0 ? z0 : mx; best = g0 ? 2 * j : best; sum += z0;
+            const bool g1 = z1 > mx; mx = g1 ? z1 : mx; best = g1 ? 2 * j + 1 : best; sum += z1;
         }
         mx /= sum;
         const int max_k = best < 0 ? -1 : (((i - BW - 1 + (best >> 1)) << 2) | (best & 1));

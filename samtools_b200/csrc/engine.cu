@@ -970,6 +970,13 @@ static int run_text(b200_engine *e, KS k_size, KW k_write, const Fmt &fmt, uint6
     return 0;
 }
 
+static uint64_t mpileup_bound(const b200_engine *e, const b200_mpileup_conf_t *c)
+{
+    const int per = 2 + (c->out_mapq ? 1 : 0) + (c->out_qpos ? 12 : 0) + (c->out_qpos5 ? 13 : 0);
+    return e->text_bound(per, 1 + 2 * (3 + c->n_star_cols));
+}
+extern "C" uint64_t b200_mpileup_text_bound(const b200_engine_t *e, const b200_mpileup_conf_t *c) { return (e && e->staged && c) ? mpileup_bound(e, c) : 0; }
+
 extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out, size_t out_cap, size_t *out_len)
 {
     if (!e || !e->staged) { if (e) snprintf(e->err, sizeof e->err, "no staged batch"); return -1; }
@@ -980,8 +987,7 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     fmt.cf.min_baseQ = c->min_baseQ; fmt.cf.all = c->all; fmt.cf.rev_del = c->rev_del; fmt.cf.no_ins = c->no_ins;
     fmt.cf.no_del = c->no_del; fmt.cf.no_ends = c->no_ends; fmt.cf.out_mapq = c->out_mapq; fmt.cf.out_qpos = c->out_qpos;
     fmt.cf.out_qpos5 = c->out_qpos5; fmt.cf.n_star_cols = c->n_star_cols;
-    const int per = 2 + (c->out_mapq ? 1 : 0) + (c->out_qpos ? 12 : 0) + (c->out_qpos5 ? 13 : 0);
-    const uint64_t bound = e->text_bound(per, 1 + 2 * (3 + c->n_star_cols)) ;
+    const uint64_t bound = mpileup_bound(e, c);
     if (e->general || e->n_files != 1 || c->out_qpos || c->out_qpos5)
         return run_text(e, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
     // ---- default (one input file, no -O columns): entry strings + gather (mpileup_ent.cuh)
@@ -1053,6 +1059,11 @@ extern "C" int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, cha
     const uint64_t ncols = (uint64_t)fmt.v.ncols;
     const uint64_t bound = ncols * (e->name.size() + 1 + 20 + (uint64_t)e->n_files * 12 + 1) + 64;
     return run_text(e, k_depth_size, k_depth_write, fmt, bound, out, out_cap, out_len);
+}
+extern "C" uint64_t b200_depth_text_bound(const b200_engine_t *e)
+{
+    if (!e || !e->staged) return 0;
+    return (uint64_t)e->ncols_max * (e->name.size() + 1 + 20 + (uint64_t)e->n_files * 12 + 1) + 64;
 }
 
 extern "C" int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b200_coverage_sums_t *sums)

@@ -28,9 +28,14 @@ using namespace b200;
 
 namespace {
 
+// One input file, decoded ONE REFERENCE SEQUENCE AT A TIME: the drivers walk the reference sequences in header order and
+// ask for the records of the sequence they are about to process (load_tid); the records of the sequences already handled
+// are released, so the resident set is one sequence per file, not the whole input.
 struct FileData {
     std::unique_ptr<AlnReader> rd;
-    std::vector<std::vector<Record>> by_tid;   // decoded records per reference sequence, file order
+    std::vector<std::vector<Record>> by_tid;   // decoded records per reference sequence, file order (only the current one is populated)
+    Record pending; bool have_pending = false, eof = false;
+    int last_tid = -1;                          // reference sequence of the last mapped record seen (sortedness check)
     int64_t n_no_tid = 0;
 };
 
@@ -44,19 +49,36 @@ bool load_file(const std::string &fn, const std::string &fai, const char *reg, F
         return false;
     }
     fd.by_tid.resize((size_t)fd.rd->header().n_ref());
-    Record r; int ret;
-    int last_tid = -1;
-    while ((ret = fd.rd->next(r)) >= 0) {
-        if (r.tid < 0 || r.tid >= (int)fd.by_tid.size()) { ++fd.n_no_tid; continue; }
-        if (!(r.flag & F_UNMAP)) {
-            // records are bucketed per reference sequence below, which would silently repair a file whose chromosomes are
-            // out of order; htslib's bam_plp_push refuses it (order within a sequence is checked by the engine's read stage)
-            if (r.tid < last_tid) { fprintf(stderr, "[%s] The input is not sorted (chromosomes out of order)\n", cmd); return false; }
-            last_tid = r.tid;
+    return true;
+}
+
+// records of reference sequence `tid` -> fd.by_tid[tid]; everything decoded for earlier sequences is dropped.
+// Returns false on a read error or when the file's reference sequences are out of order.
+bool load_tid(FileData &fd, int tid, const char *cmd)
+{
+    if (tid < 0 || tid >= (int)fd.by_tid.size()) return true;
+    for (int t = 0; t < tid; ++t) if (!fd.by_tid[(size_t)t].empty()) std::vector<Record>().swap(fd.by_tid[(size_t)t]);
+    std::vector<Record> &dst = fd.by_tid[(size_t)tid];
+    for (;;) {
+        if (!fd.have_pending) {
+            if (fd.eof) break;
+            const int ret = fd.rd->next(fd.pending);
+            if (ret == -1) { fd.eof = true; break; }
+            if (ret < -1) { fprintf(stderr, "samtools %s: error reading from input file\n", cmd); return false; }
+            fd.have_pending = true;
         }
-        fd.by_tid[(size_t)r.tid].push_back(std::move(r));
+        Record &r = fd.pending;
+        if (r.tid < 0 || r.tid >= (int)fd.by_tid.size()) { ++fd.n_no_tid; fd.have_pending = false; continue; }
+        if (!(r.flag & F_UNMAP)) {
+            // records are handed out per reference sequence, which would silently repair a file whose chromosomes are
+            // out of order; htslib's bam_plp_push refuses it (order within a sequence is checked by the engine's read stage)
+            if (r.tid < fd.last_tid) { fprintf(stderr, "[%s] The input is not sorted (chromosomes out of order)\n", cmd); return false; }
+            fd.last_tid = r.tid;
+        }
+        if (r.tid > tid) break;                       // belongs to a later sequence: stays pending
+        if (r.tid == tid) dst.push_back(std::move(r));
+        fd.have_pending = false;                      // (an unmapped straggler of an earlier sequence is dropped)
     }
-    if (ret < -1) { fprintf(stderr, "samtools %s: error reading from input file\n", cmd); return false; }
     return true;
 }
 
@@ -87,6 +109,38 @@ bool window_for(const PackedBatch &pb, int64_t beg, int64_t end, bool all, int64
 }
 
 void write_all(FILE *fp, const std::vector<char> &buf, size_t n) { if (n) fwrite(buf.data(), 1, n, fp); }
+
+// ---- column windows ------------------------------------------------------------------------------------------------
+// The engine addresses columns as 32-bit offsets from the window start and takes < 4 GiB of read payload per staged
+// batch, so the drivers cut a reference sequence into windows of at most window_cols() columns.  A window [wb,we)
+// stages every record that overlaps it -- pos < we && endpos > wb, the rule a `-r` run applies (bam_plcmd.c:550-554,609)
+// -- so a read reaching in from the left is staged again ("halo"); the engine reports only columns inside the window.
+// Per-read work (filters, BAQ) is simply repeated for halo reads; a mate pair whose overlap lies in the window has both
+// mates staged, so the overlap tweak sees what an unsplit run sees.  NOT carried across a window edge: the buffer
+// occupancy the -d max-depth rule of bam_plp_push looks at (only matters when a column holds more reads than -d).
+int64_t window_cols()
+{
+    static int64_t w = 0;
+    if (!w) { const char *s = getenv("B200_WINDOW_COLS"); w = s ? atoll(s) : (1LL << 24); if (w < 1) w = 1; if (w > (1LL << 30)) w = 1LL << 30; }
+    return w;
+}
+// records of v (sorted by pos) overlapping [wb,we); `lo` is a cursor that only moves forward across successive windows
+void window_records(const std::vector<Record> &v, size_t &lo, int64_t wb, int64_t we, std::vector<size_t> &out)
+{
+    out.clear();
+    while (lo < v.size() && v[lo].endpos() <= wb) ++lo;
+    for (size_t j = lo; j < v.size() && v[j].pos < we; ++j) if (v[j].endpos() > wb) out.push_back(j);
+}
+// first / one-past-last reference position touched by the records of a contig (over all files)
+bool records_extent(const std::vector<FileData> &fd, int tid, int64_t &first, int64_t &last)
+{
+    bool any = false; first = POS_MAX; last = 0;
+    for (const FileData &f : fd) {
+        if (tid >= (int)f.by_tid.size()) continue;
+        for (const Record &r : f.by_tid[(size_t)tid]) { any = true; if (r.pos < first) first = r.pos; const int64_t e = r.endpos(); if (e > last) last = e; }
+    }
+    return any;
+}
 
 // ----------------------------------------------------------------------------- mpileup
 struct MpOpts {
@@ -188,50 +242,89 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
     std::vector<char> out;
     std::vector<int64_t> bb, be;
     const int nref = h.n_ref();
+    std::vector<size_t> sel; std::vector<size_t> cursor((size_t)nfn);
+    std::vector<std::vector<uint8_t>> hbits((size_t)nfn);   // host bits of the contig's records, decided ONCE (the BQ:Z path edits the record)
+    // one window [wb,we) of contig tid: stage the overlapping records, return the stage statistics
+    auto stage_window = [&](int tid, bool with_reads, int64_t wb, int64_t we, const std::string *ref, b200_stage_stats_t &st) -> int {
+        const std::string &name = h.names[(size_t)tid];
+        pb.clear();
+        for (int i = 0; i < nfn; ++i) {
+            pb.begin_file();
+            if (with_reads && tid < (int)fd[(size_t)i].by_tid.size()) {
+                std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
+                window_records(v, cursor[(size_t)i], wb, we, sel);
+                for (size_t j : sel) pb.add(v[j], hbits[(size_t)i][j], o.overlaps);
+            }
+        }
+        pb.finish();
+        b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], name, ref);
+        sc.beg = wb; sc.end = we;
+        if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools mpileup: %s\n", b200_last_error(eng.e)); return -1; }
+        return 0;
+    };
     auto process_tid = [&](int tid, bool with_reads) -> int {
         // returns 1 when rows were requested and produced, 0 when the contig has no pileup column, <0 on error
         const std::string &name = h.names[(size_t)tid];
         const std::string *ref = nullptr;
         if (o.fa) { int fi = o.fa->find(name); if (fi >= 0) ref = &o.fa->seqs[(size_t)fi]; }
-        pb.clear();
-        for (int i = 0; i < nfn; ++i) {
-            pb.begin_file();
-            if (with_reads && tid < (int)fd[(size_t)i].by_tid.size())
-                for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) pb.add(r, mp_host_bits(o, h, r, ref != nullptr), o.overlaps);
-        }
-        pb.finish();
-        b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], name, ref);
-        b200_stage_stats_t st;
-        if (!window_for(pb, o.reg ? beg0 : 0, o.reg ? end0 : POS_MAX, o.all != 0, h.lens[(size_t)tid], sc.beg, sc.end)) {
-            fprintf(stderr, "samtools mpileup: contig %s needs more than one 2^31-column window with -a (not supported yet)\n", name.c_str());
-            return -1;
-        }
-        if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools mpileup: %s\n", b200_last_error(eng.e)); return -1; }
-        if (with_reads && st.n_kept_in_window == 0) return 0;
         if (o.bed) { o.bed->merged(name, bb, be); mc.bed_beg = bb.data(); mc.bed_end = be.data(); mc.n_bed = (int)bb.size(); mc.bed_active = 1; }
-        if (o.gl) {
-            int64_t ncols = 0; const size_t cap = (size_t)st.n_cols + 16;
-            std::vector<int64_t> cpos(cap); std::vector<int32_t> nb(cap * (size_t)nfn); std::vector<float> qs(cap * (size_t)nfn * 4), p25(cap * (size_t)nfn * 25);
-            if (b200_glf(eng.e, o.min_baseQ, &ncols, cpos.data(), nb.data(), qs.data(), p25.data(), cap) != 0) { fprintf(stderr, "samtools gl: %s\n", b200_last_error(eng.e)); return -1; }
-            for (int64_t k = 0; k < ncols; ++k) {
-                const int64_t p = cpos[(size_t)k];
-                if (o.bed && !o.bed->overlap(name, p, p + 1)) continue;
-                fprintf(fp, "%s\t%lld\t%c", name.c_str(), (long long)p + 1, (ref && p < (int64_t)ref->size()) ? (*ref)[(size_t)p] : 'N');
-                for (int f = 0; f < nfn; ++f) {
-                    const size_t d = (size_t)k * (size_t)nfn + (size_t)f;
-                    fprintf(fp, "\t%d", nb[d] < 0 ? 0 : nb[d]);
-                    for (int j = 0; j < 4; ++j) fprintf(fp, "\t%.9g", qs[d * 4 + (size_t)j]);
-                    for (int j = 0; j < 25; ++j) fprintf(fp, "\t%.9g", p25[d * 25 + (size_t)j]);
-                }
-                fputc('\n', fp);
-            }
-            return 1;
+        // columns to visit: the region, cut down to the span of the records unless empty rows are wanted (-a)
+        const int64_t rb = o.reg ? beg0 : 0, re = o.reg ? end0 : POS_MAX, tid_len = h.lens[(size_t)tid];
+        int64_t first = 0, last = 0;
+        const bool have = with_reads && records_extent(fd, tid, first, last);
+        int64_t lo_col = rb, hi_col = std::min(re, tid_len);
+        if (have) { if (!o.all) { lo_col = std::max(rb, first); hi_col = std::min(re, last); } else hi_col = std::max(hi_col, std::min(re, last)); }
+        else if (with_reads) return 0;
+        for (int i = 0; i < nfn; ++i) {
+            hbits[(size_t)i].clear();
+            if (with_reads && tid < (int)fd[(size_t)i].by_tid.size())
+                for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) hbits[(size_t)i].push_back(mp_host_bits(o, h, r, ref != nullptr));
         }
-        size_t need = 0;
-        int rc = b200_mpileup_text(eng.e, &mc, nullptr, 0, &need);      // format in HBM, learn the size
-        if (rc == 0) { out.resize(need + 1); rc = b200_mpileup_text(eng.e, &mc, out.data(), out.size(), &need); }
-        if (rc != 0) { fprintf(stderr, "samtools mpileup: %s\n", b200_last_error(eng.e)); return -1; }
-        write_all(fp, out, need);
+        const int64_t W = window_cols();
+        // the first window with a pileup column decides whether the contig is reported at all (its empty -a rows before that
+        // column included), so find it before anything is written
+        int64_t first_hit = -1;
+        if (with_reads) {
+            std::fill(cursor.begin(), cursor.end(), 0);
+            for (int64_t wb = lo_col; wb < hi_col; wb += W) {
+                b200_stage_stats_t st;
+                if (stage_window(tid, true, wb, std::min(wb + W, hi_col), ref, st) != 0) return -1;
+                if (st.n_kept_in_window > 0) { first_hit = wb; break; }
+            }
+            if (first_hit < 0) return 0;
+        }
+        std::fill(cursor.begin(), cursor.end(), 0);
+        for (int64_t wb = lo_col; wb < hi_col || (!with_reads && wb == lo_col); wb += W) {
+            const int64_t we = std::max(std::min(wb + W, hi_col), wb);
+            b200_stage_stats_t st;
+            if (stage_window(tid, with_reads, wb, we, ref, st) != 0) return -1;
+            if (with_reads && !o.all && st.n_kept_in_window == 0) continue;
+            if (o.gl) {
+                int64_t ncols = 0; const size_t cap = (size_t)st.n_cols + 16;
+                std::vector<int64_t> cpos(cap); std::vector<int32_t> nb(cap * (size_t)nfn); std::vector<float> qs(cap * (size_t)nfn * 4), p25(cap * (size_t)nfn * 25);
+                if (b200_glf(eng.e, o.min_baseQ, &ncols, cpos.data(), nb.data(), qs.data(), p25.data(), cap) != 0) { fprintf(stderr, "samtools gl: %s\n", b200_last_error(eng.e)); return -1; }
+                for (int64_t k = 0; k < ncols; ++k) {
+                    const int64_t p = cpos[(size_t)k];
+                    if (o.bed && !o.bed->overlap(name, p, p + 1)) continue;
+                    fprintf(fp, "%s\t%lld\t%c", name.c_str(), (long long)p + 1, (ref && p < (int64_t)ref->size()) ? (*ref)[(size_t)p] : 'N');
+                    for (int f = 0; f < nfn; ++f) {
+                        const size_t d = (size_t)k * (size_t)nfn + (size_t)f;
+                        fprintf(fp, "\t%d", nb[d] < 0 ? 0 : nb[d]);
+                        for (int j = 0; j < 4; ++j) fprintf(fp, "\t%.9g", qs[d * 4 + (size_t)j]);
+                        for (int j = 0; j < 25; ++j) fprintf(fp, "\t%.9g", p25[d * 25 + (size_t)j]);
+                    }
+                    fputc('\n', fp);
+                }
+                continue;
+            }
+            const size_t bound = (size_t)b200_mpileup_text_bound(eng.e, &mc);
+            if (out.size() < bound + 64) out.resize(bound + 64);
+            size_t need = 0;
+            int rc = b200_mpileup_text(eng.e, &mc, out.data(), out.size(), &need);      // format and fetch in one call
+            if (rc != 0) { fprintf(stderr, "samtools mpileup: %s\n", b200_last_error(eng.e)); return -1; }
+            write_all(fp, out, need);
+            if (!with_reads) break;
+        }
         return 1;
     };
 
@@ -241,7 +334,7 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
         for (int tid = 0; tid < nref; ++tid) {
             if (o.reg && tid != tid0) continue;
             bool has = false;
-            for (int i = 0; i < nfn; ++i) if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+            for (int i = 0; i < nfn; ++i) { if (!load_tid(fd[(size_t)i], tid, "mpileup")) return 1; if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true; }
             if (!has) continue;
             int rc = process_tid(tid, true);
             if (rc < 0) return 1;
@@ -253,7 +346,7 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
         // -aa without a region: every contig, covered or not (bam_plcmd.c:612-636, :886-909)
         for (int tid = 0; tid < nref; ++tid) {
             bool has = false;
-            for (int i = 0; i < nfn; ++i) if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+            for (int i = 0; i < nfn; ++i) { if (!load_tid(fd[(size_t)i], tid, "mpileup")) return 1; if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true; }
             int rc = has ? process_tid(tid, true) : 0;
             if (rc < 0) return 1;
             if (rc == 0 && !o.gl) { if (process_tid(tid, false) < 0) return 1; }
@@ -398,65 +491,88 @@ int main_depth(int argc, char **argv)
     // i.e. across reference sequences, and only records that pass the read filters take part.  It is replayed here
     // in file order (name hashing is host work anyway) and handed to the engine as one clip coordinate per record.
     std::vector<std::vector<std::vector<int64_t>>> clips((size_t)nfn);
-    if (remove_overlaps) {
-        auto qlen_used = [](const Record &r) -> int64_t {
-            int64_t l;
-            const int n = (int)r.cigar.size();
-            if (r.l_qseq) {
-                l = r.l_qseq; int kl, kr;
-                for (kl = 0; kl < n; kl++) { if ((r.cigar[(size_t)kl] & 0xf) == 4) l -= r.cigar[(size_t)kl] >> 4; else break; }
-                for (kr = n - 1; kr > kl; kr--) { if ((r.cigar[(size_t)kr] & 0xf) == 4) l -= r.cigar[(size_t)kr] >> 4; else break; }
-            } else { l = 0; for (uint32_t c : r.cigar) { int op = c & 0xf; if (op == 0 || op == 1 || op == 7 || op == 8) l += c >> 4; } }
-            return l;
-        };
-        for (int i = 0; i < nfn; ++i) {
-            std::unordered_map<std::string, int64_t> seen;
-            clips[(size_t)i].resize(fd[(size_t)i].by_tid.size());
-            for (size_t t = 0; t < fd[(size_t)i].by_tid.size(); ++t) {
-                auto &cv = clips[(size_t)i][t];
-                for (const Record &r : fd[(size_t)i].by_tid[t]) {
-                    int64_t clip = 0;
-                    const bool pass = !(r.flag & flag) && !(incl && (r.flag & incl) == 0) && (r.flag & require) == require &&
-                                      r.mapq >= min_mqual && !(min_len && qlen_used(r) < min_len);
-                    if (pass && (r.flag & F_PAIRED) && !(r.flag & F_MUNMAP)) {
-                        auto it = seen.find(r.qname);
-                        if (it == seen.end()) { const int64_t e = r.endpos(); if (r.mpos == -1 || (r.tid == r.mtid && r.mpos <= e)) seen.emplace(r.qname, e); }
-                        else { clip = it->second; seen.erase(it); }
-                    }
-                    cv.push_back(clip);
-                }
+    std::vector<std::unordered_map<std::string, int64_t>> seen((size_t)nfn);   // the per-file name hash, alive across reference sequences
+    auto qlen_used = [](const Record &r) -> int64_t {
+        int64_t l;
+        const int n = (int)r.cigar.size();
+        if (r.l_qseq) {
+            l = r.l_qseq; int kl, kr;
+            for (kl = 0; kl < n; kl++) { if ((r.cigar[(size_t)kl] & 0xf) == 4) l -= r.cigar[(size_t)kl] >> 4; else break; }
+            for (kr = n - 1; kr > kl; kr--) { if ((r.cigar[(size_t)kr] & 0xf) == 4) l -= r.cigar[(size_t)kr] >> 4; else break; }
+        } else { l = 0; for (uint32_t c : r.cigar) { int op = c & 0xf; if (op == 0 || op == 1 || op == 7 || op == 8) l += c >> 4; } }
+        return l;
+    };
+    // records of reference sequence tid of file i are in: replay the hash over them (file order = the order the reference sees them)
+    auto replay_clips = [&](int i, int tid) {
+        if (!remove_overlaps || tid >= (int)fd[(size_t)i].by_tid.size()) return;
+        clips[(size_t)i].resize(fd[(size_t)i].by_tid.size());
+        for (int t = 0; t < tid; ++t) std::vector<int64_t>().swap(clips[(size_t)i][(size_t)t]);
+        auto &cv = clips[(size_t)i][(size_t)tid];
+        cv.clear();
+        for (const Record &r : fd[(size_t)i].by_tid[(size_t)tid]) {
+            int64_t clip = 0;
+            const bool pass = !(r.flag & flag) && !(incl && (r.flag & incl) == 0) && (r.flag & require) == require &&
+                              r.mapq >= min_mqual && !(min_len && qlen_used(r) < min_len);
+            if (pass && (r.flag & F_PAIRED) && !(r.flag & F_MUNMAP)) {
+                auto it = seen[(size_t)i].find(r.qname);
+                if (it == seen[(size_t)i].end()) { const int64_t e = r.endpos(); if (r.mpos == -1 || (r.tid == r.mtid && r.mpos <= e)) seen[(size_t)i].emplace(r.qname, e); }
+                else { clip = it->second; seen[(size_t)i].erase(it); }
             }
+            cv.push_back(clip);
         }
-    }
-    auto process_tid = [&](int tid, bool with_reads) -> int {
-        const std::string &name = h.names[(size_t)tid];
+    };
+    std::vector<size_t> sel; std::vector<size_t> cursor((size_t)nfn);
+    auto stage_window = [&](int tid, bool with_reads, int64_t wb, int64_t we, b200_stage_stats_t &st) -> int {
         pb.clear();
         for (int i = 0; i < nfn; ++i) {
             pb.begin_file();
             if (with_reads && tid < (int)fd[(size_t)i].by_tid.size()) {
-                size_t k = 0;
-                for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) {
-                    pb.add(r, 0, false);
-                    if (remove_overlaps) pb.depth_clip.push_back(clips[(size_t)i][(size_t)tid][k]);
-                    ++k;
+                std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
+                window_records(v, cursor[(size_t)i], wb, we, sel);
+                for (size_t j : sel) {
+                    pb.add(v[j], 0, false);
+                    if (remove_overlaps) pb.depth_clip.push_back(clips[(size_t)i][(size_t)tid][j]);
                 }
             }
         }
         pb.finish();
-        b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], name, nullptr);
-        b200_stage_stats_t st;
-        if (!window_for(pb, reg ? beg0 : 0, reg ? end0 : POS_MAX, all_pos != 0, h.lens[(size_t)tid], sc.beg, sc.end)) {
-            fprintf(stderr, "samtools depth: contig %s needs more than one 2^31-column window with -a (not supported yet)\n", name.c_str());
-            return -1;
-        }
+        b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], h.names[(size_t)tid], nullptr);
+        sc.beg = wb; sc.end = we;
         if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools depth: %s\n", b200_last_error(eng.e)); return -1; }
-        if (with_reads && st.n_kept == 0) return 0;   // no record survives the filters: the contig is never "seen"
+        return 0;
+    };
+    auto process_tid = [&](int tid, bool with_reads) -> int {
+        const std::string &name = h.names[(size_t)tid];
         if (bed) { bed->merged(name, bb, be); dc.bed_beg = bb.data(); dc.bed_end = be.data(); dc.n_bed = (int)bb.size(); dc.bed_active = 1; }
-        size_t need = 0;
-        int rc = b200_depth_text(eng.e, &dc, nullptr, 0, &need);
-        if (rc == 0) { out.resize(need + 1); rc = b200_depth_text(eng.e, &dc, out.data(), out.size(), &need); }
-        if (rc != 0) { fprintf(stderr, "samtools depth: %s\n", b200_last_error(eng.e)); return -1; }
-        write_all(fp, out, need);
+        const int64_t rb = reg ? beg0 : 0, re = reg ? end0 : POS_MAX, tid_len = h.lens[(size_t)tid];
+        int64_t first = 0, last = 0;
+        const bool have = with_reads && records_extent(fd, tid, first, last);
+        int64_t lo_col = rb, hi_col = std::min(re, tid_len);
+        if (have) { if (!all_pos) { lo_col = std::max(rb, first); hi_col = std::min(re, last); } else hi_col = std::max(hi_col, std::min(re, last)); }
+        else if (with_reads) return 0;
+        const int64_t W = window_cols();
+        if (with_reads) {   // a contig no record of which survives the filters is never "seen" (bam2depth.c:255-263): decide before writing
+            bool seen = false;
+            std::fill(cursor.begin(), cursor.end(), 0);
+            for (int64_t wb = lo_col; wb < hi_col && !seen; wb += W) {
+                b200_stage_stats_t st;
+                if (stage_window(tid, true, wb, std::min(wb + W, hi_col), st) != 0) return -1;
+                seen = st.n_kept > 0;
+            }
+            if (!seen) return 0;
+        }
+        std::fill(cursor.begin(), cursor.end(), 0);
+        for (int64_t wb = lo_col; wb < hi_col || (!with_reads && wb == lo_col); wb += W) {
+            const int64_t we = std::max(std::min(wb + W, hi_col), wb);
+            b200_stage_stats_t st;
+            if (stage_window(tid, with_reads, wb, we, st) != 0) return -1;
+            const size_t bound = (size_t)b200_depth_text_bound(eng.e);
+            if (out.size() < bound + 64) out.resize(bound + 64);
+            size_t need = 0;
+            if (b200_depth_text(eng.e, &dc, out.data(), out.size(), &need) != 0) { fprintf(stderr, "samtools depth: %s\n", b200_last_error(eng.e)); return -1; }
+            write_all(fp, out, need);
+            if (!with_reads) break;
+        }
         return 1;
     };
     const int nref = h.n_ref();
@@ -464,7 +580,11 @@ int main_depth(int argc, char **argv)
     for (int tid = 0; tid < nref; ++tid) {
         if (reg && tid != tid0) continue;
         bool has = false;
-        for (int i = 0; i < nfn; ++i) if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+        for (int i = 0; i < nfn; ++i) {
+            if (!load_tid(fd[(size_t)i], tid, "depth")) return 1;
+            replay_clips(i, tid);
+            if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+        }
         int rc = has ? process_tid(tid, true) : 0;
         if (rc < 0) return 1;
         if (rc > 0) any = true;
@@ -540,25 +660,41 @@ int main_coverage(int argc, char **argv)
         rw.beg = 0; rw.end = h.lens[(size_t)tid];
         if (reg && tid == tid0) { rw.beg = beg0; rw.end = end0 == POS_MAX ? h.lens[(size_t)tid] : end0; }
         bool has = false;
-        for (i = 0; i < nfn; ++i) if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true;
+        for (i = 0; i < nfn; ++i) { if (!load_tid(fd[(size_t)i], tid, "coverage")) return 1; if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true; }
         if (!has) continue;
-        pb.clear();
-        for (i = 0; i < nfn; ++i) {
-            pb.begin_file();
-            if (tid < (int)fd[(size_t)i].by_tid.size()) for (Record &r : fd[(size_t)i].by_tid[(size_t)tid]) pb.add(r, 0, false);
-        }
-        pb.finish();
-        b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], h.names[(size_t)tid], nullptr);
-        sc.beg = rw.beg; sc.end = rw.end;
-        b200_stage_stats_t st;
-        if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools coverage: %s\n", b200_last_error(eng.e)); return 1; }
-        rw.n_sel = st.n_selected_reads; rw.sum_mq = st.summed_mapq;
-        // a column exists as soon as one kept read has a non-empty reference span (before the region test)
-        if (st.n_kept > 0) {
-            if (b200_coverage(eng.e, &cc, &rw.s) != 0) { fprintf(stderr, "samtools coverage: %s\n", b200_last_error(eng.e)); return 1; }
-            rw.covered = true;   // refined below: zero-span-only contigs are vanishingly rare
-            order.push_back(tid);
-            if (rw.s.missing_qual) warn = true;
+        // column windows of [rw.beg, rw.end): the sums add up.  Every record is counted once in the read statistics
+        // (coverage.c:185-193): a read that reaches in from the previous window is staged again as halo (B200_RB_HALO);
+        // the first / last window also take the records that lie before / beyond the region.
+        const int64_t W = window_cols();
+        std::vector<size_t> sel, cursor((size_t)nfn, 0);
+        for (int64_t wb = rw.beg; wb < rw.end || wb == rw.beg; wb += W) {
+            const bool first_w = wb == rw.beg, last_w = wb + W >= rw.end;
+            const int64_t we = last_w ? std::max(rw.end, wb) : wb + W;
+            pb.clear();
+            for (i = 0; i < nfn; ++i) {
+                pb.begin_file();
+                if (tid >= (int)fd[(size_t)i].by_tid.size()) continue;
+                std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
+                window_records(v, cursor[(size_t)i], first_w ? INT64_MIN : wb, last_w ? POS_MAX : we, sel);
+                for (size_t j : sel) pb.add(v[j], (uint8_t)((!first_w && v[j].pos < wb) ? B200_RB_HALO : 0), false);
+            }
+            pb.finish();
+            if (pb.pos.empty()) { if (last_w) break; continue; }
+            b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], h.names[(size_t)tid], nullptr);
+            sc.beg = wb; sc.end = we;
+            b200_stage_stats_t st;
+            if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools coverage: %s\n", b200_last_error(eng.e)); return 1; }
+            rw.n_sel += st.n_selected_reads; rw.sum_mq += st.summed_mapq;
+            // a column exists as soon as one kept read has a non-empty reference span (before the region test)
+            if (st.n_kept > 0) {
+                b200_coverage_sums_t ws;
+                if (b200_coverage(eng.e, &cc, &ws) != 0) { fprintf(stderr, "samtools coverage: %s\n", b200_last_error(eng.e)); return 1; }
+                rw.s.n_covered_bases += ws.n_covered_bases; rw.s.summed_coverage += ws.summed_coverage; rw.s.summed_baseQ += ws.summed_baseQ;
+                rw.s.quality_bases += ws.quality_bases; rw.s.missing_qual += ws.missing_qual;
+                if (!rw.covered) { rw.covered = true; order.push_back(tid); }   // refined: zero-span-only contigs are vanishingly rare
+                if (ws.missing_qual) warn = true;
+            }
+            if (last_w) break;
         }
     }
     auto print_row = [&](int tid) {

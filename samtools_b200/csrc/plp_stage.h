@@ -82,7 +82,8 @@ PLP_HD void stage_prep1(const RawSoA &r, const b200_stage_conf_t &cf, int64_t i,
             if (l < cf.d_min_len) alive = false;
         }
     } else {  // coverage
-        PLP_ADD64(&acc->n_reads, 1);
+        const bool counted = !(rb & B200_RB_HALO);   // a read staged again by the next column window is counted once
+        if (counted) PLP_ADD64(&acc->n_reads, 1);
         if (cf.rflag_filter && (fl & cf.rflag_filter)) alive = false;
         if (cf.rflag_require && !(fl & cf.rflag_require)) alive = false;
         if (r.mapq[i] < cf.min_mq) alive = false;
@@ -91,7 +92,7 @@ PLP_HD void stage_prep1(const RawSoA &r, const b200_stage_conf_t &cf, int64_t i,
             for (int k = 0; k < n; k++) { int op = cg[k] & 0xf; if (op == OP_M || op == OP_I || op == OP_S || op == OP_EQ || op == OP_X) l += cg[k] >> 4; }
             if (l < cf.c_min_len) alive = false;
         }
-        if (alive) { PLP_ADD64(&acc->n_selected, 1); PLP_ADD64(&acc->summed_mapq, r.mapq[i]); }
+        if (alive && counted) { PLP_ADD64(&acc->n_selected, 1); PLP_ADD64(&acc->summed_mapq, r.mapq[i]); }
         if (fl & 4) alive = false;   // bam_plp_push ignores unmapped reads
     }
     state[i] = alive ? ST_ALIVE : ST_DEAD;

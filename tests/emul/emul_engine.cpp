@@ -284,6 +284,17 @@ int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out,
     return emit(e, s, out, cap, out_len);
 }
 
+uint64_t b200_mpileup_text_bound(const b200_engine_t *e, const b200_mpileup_conf_t *c)
+{
+    size_t n = 0;
+    return b200_mpileup_text(const_cast<b200_engine_t *>(e), c, nullptr, 0, &n) == 0 ? n + 64 : 0;
+}
+int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, char *out, size_t cap, size_t *out_len);
+uint64_t b200_depth_text_bound(const b200_engine_t *e)
+{
+    // every row: name, tab, position, (tab, depth) per file, newline
+    return (uint64_t)e->ncols_max * (e->name.size() + 1 + 20 + (uint64_t)e->b.n_files * 12 + 1) + 64;
+}
 int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *c, char *out, size_t cap, size_t *out_len)
 {
     View v; fill_view(e, v, c->bed_beg, c->bed_end, c->n_bed, c->bed_active, c->all);

@@ -40,3 +40,22 @@ def test_c1_ex1_host_path(cmd, emul_bin, oracle_bin, corpus):
     want = subprocess.run(f'{oracle_bin} {cmd}', shell=True, cwd=cwd, capture_output=True)
     got = subprocess.run(f'{emul_bin} {cmd}', shell=True, cwd=cwd, capture_output=True)
     assert len(want.stdout) > 1000 and got.stdout == want.stdout
+
+
+def test_column_windows_with_halo(emul_bin, oracle_bin, corpus, monkeypatch):
+    """The drivers cut every reference sequence into column windows and stage, per window, the records overlapping it
+    (halo = reads reaching in from the left, the -r rule bam_plcmd.c:550-554,609).  With 97-column windows every golden
+    mpileup / depth / coverage case crosses dozens of window edges -- reads, mate overlaps, deletions, -a / -aa rows,
+    BED filters, depth -s clips, coverage read counts -- and must still reproduce the reference's bytes."""
+    from concurrent.futures import ThreadPoolExecutor
+    monkeypatch.setenv('B200_WINDOW_COLS', '97')
+    todo = [c for c in CASES if not c['skip'] and '>' not in c['cmd']]
+
+    def run(c):
+        ok, out, err = golden_cases.run_case(c, emul_bin, oracle_bin, corpus)
+        if not ok and (b'BAQ kernel is not emulated' in err or b'not available on the device path' in err):
+            return None
+        return None if ok else (c['id'], c['cmd'], err[-200:])
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        bad = [r for r in ex.map(run, todo) if r]
+    assert not bad, bad[:3]

@@ -55,6 +55,23 @@ def test_reference_golden_on_gpu(case, golden_results):
     assert ok, f"{case['cmd']}\nstderr: {err[-400:]!r}\nstdout head: {out[:300]!r}"
 
 
+def test_column_windows_on_gpu(cli, oracle_bin, corpus, monkeypatch):
+    """the drivers' column windows (halo reads staged again, tests/test_emul_golden.py::test_column_windows_with_halo) through
+    the CUDA engine: every golden case with 97-column windows, BAQ included"""
+    from concurrent.futures import ThreadPoolExecutor
+    monkeypatch.setenv('B200_WINDOW_COLS', '97')
+    todo = [c for c in CASES if not c['skip'] and '>' not in c['cmd']]
+
+    def run(c):
+        ok, out, err = golden_cases.run_case(c, cli, oracle_bin, corpus)
+        if not ok and b'not available on the device path' in err:
+            return None
+        return None if ok else (c['id'], c['cmd'], err[-200:])
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        bad = [r for r in ex.map(run, todo) if r]
+    assert not bad, bad[:3]
+
+
 # ---------------------------------------------------------------- synthetic, C ABI vs oracle
 @pytest.fixture(scope='module')
 def synth_set(tmp_path_factory, oracle_bin):
