@@ -411,16 +411,16 @@ def main():
     if rank == 0:
         kms = float(np.mean(kernel_ms))
         size_ms, scan_ms, write_ms = [float(x) for x in np.mean(np.array(parts_ms), axis=0)]
-        # dominant kernel = the write pass: it re-reads every staged read (descriptor, qualities, bases) and
-        # writes every text byte once -> its algorithmic bytes are bytes_in + bytes_out
-        alg = bytes_in + out_len
-        achieved = alg / (write_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            if abs(tj.get('region_mb', 0) - args.region_mb) < 1e-9:
-                traffic = tj.get('write_kernel_dram_bytes')
+        # column stage = entry pass (read-major: every read's bases -> 16-bit entries + the line-length sums) + tile scan + gather
+        # (column-major: entries -> text).  The roofline names the slower of the two passes.  Algorithmic bytes: the
+        # gather consumes every read base once and writes every text byte once -> bytes_in + bytes_out; the entry pass reads the
+        # staged reads once -> bytes_in (its entry strings are an intermediate, not algorithmic traffic)
+        if write_ms >= size_ms:
+            dom, alg, dom_ms = 'k_mp_gather (entry strings -> text)', bytes_in + out_len, write_ms
+        else:
+            dom, alg, dom_ms = 'k_mp_entries + k_ss_scan + k_ss_cols (reads -> entry strings, line sizes)', bytes_in, size_ms
+        achieved = alg / (dom_ms * 1e-3) / 1e9
+        traffic = None                                   # measured under ncu only (profiles/), never in a timed run
         value = world * ncols * args.steps / dt
         e2e = world * ncols * args.steps / dt_e2e
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -429,12 +429,12 @@ def main():
                 'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(out_len), 'ms_per_step': 1e3 * dt_e2e / args.steps,
                         'handles': n_h},
                 'gpu_launches': int(launches),
-                'roofline': {'bound': 'hbm', 'kernel': 'mpileup write pass', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                              'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': int(alg),
-                             'bytes_in': int(bytes_in), 'bytes_out': int(out_len), 'kernel_ms': write_ms,
-                             'step_kernels_ms': {'read_stage': float(np.mean(stage_ms)), 'size_pass': size_ms, 'tile_offset_scan': scan_ms,
-                                                 'write_pass': write_ms, 'column_stage_total': kms, 'total': kms + float(np.mean(stage_ms))},
-                             'step_frac': alg / ((kms + float(np.mean(stage_ms))) * 1e-3) / 1e9 / peak},
+                             'bytes_in': int(bytes_in), 'bytes_out': int(out_len), 'kernel_ms': dom_ms,
+                             'step_kernels_ms': {'read_stage': float(np.mean(stage_ms)), 'entry_pass': size_ms, 'tile_offset_scan': scan_ms,
+                                                 'gather': write_ms, 'column_stage_total': kms, 'total': kms + float(np.mean(stage_ms))},
+                             'step_frac': (bytes_in + out_len) / ((kms + float(np.mean(stage_ms))) * 1e-3) / 1e9 / peak},
                 'reads_per_step_per_gpu': n_reads}
 
     # ------------------------------------------------------------------------------------ further BASELINE configurations
@@ -471,7 +471,7 @@ def main():
             'workload': f'same {args.region_mb:g} Mb window with its FASTA: `mpileup -a -f` (BAQ = sam_prob_realn on every read, overlap removal, -Q13)',
             'value': world * ncols * msteps / dtb, 'unit': UNIT, 'ms_per_step': 1e3 * dtb / msteps, 'steps': msteps, 'bytes_out': int(blen),
             'reads_per_s_baq_kernels': n_reads / (bms * 1e-3),
-            'roofline': {'bound': 'fp64 (non-fused: BAQ must not contract a*b+c)', 'kernel': 'BAQ kernels (k_baq_plan + k_baq_*)', 'achieved': ach / 1e12,
+            'roofline': {'bound': 'fp64 (non-fused: BAQ must not contract a*b+c)', 'kernel': 'BAQ kernels (k_baq_plan + k_baq_reg)', 'achieved': ach / 1e12,
                          'peak': FP64_NONFMA_PEAK / 1e12, 'unit': 'Top/s (FP64, non-FMA)', 'frac': ach / FP64_NONFMA_PEAK,
                          'peak_source': 'nominal: 148 SMs x 64 FP64 lanes x 1.965 GHz (no measured FP64 figure in MEASURED_PEAKS.json)',
                          'algorithmic_ops_per_launch': ops, 'kernel_ms': bms, 'traffic': None,

@@ -576,9 +576,11 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     e->smem_text = 24 * 1024;
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
+    s = getenv("B200_PLP_GATHER_OCC"); e->gather_occ = s ? atoi(s) : 6;   // A/B: gather kernel built for 6 (80 registers) or 8 (64, small spills) CTAs per SM
     s = getenv("B200_PLP_GENERAL"); e->general = s ? atoi(s) : 0;   // 1: general mpileup path (thread-per-column size + write) for every configuration
     if (e->smem_text + 16 > 48 * 1024) {   // the attribute is per function and process-wide: only ever raise it (another handle may use more)
-        cudaFuncSetAttribute(k_mp_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_mp_gather<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_mp_gather<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_mpileup_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_depth_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e->smem_text > 200 * 1024 - 16) e->smem_text = 200 * 1024 - 16;
@@ -1016,8 +1018,9 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     {
         const int64_t want_blocks = (e->n * 32 + 255) / 256;
         const int rb = (int)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)e->n_sm * 16));
-        k_mp_entries<<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, e->has_ref ? e->ref_codes : nullptr, e->ss_diff, e->ss_fail, e->ss_extra,
-                                                e->ent, e->ent2, e->d_misc + 3, e->desc); e->launches++;
+        if (e->has_ref) k_mp_entries<true><<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, e->ref_codes, e->ss_diff, e->ss_fail, e->ss_extra, e->ent, e->ent2, e->d_misc + 3, e->desc);
+        else k_mp_entries<false><<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, nullptr, e->ss_diff, e->ss_fail, e->ss_extra, e->ent, e->ent2, e->d_misc + 3, e->desc);
+        e->launches++;
         k_ss_scan<<<nbs, 256, 0, e->stream>>>(e->ss_diff, e->ss_nplp, ncols + 1, e->status2, (uint32_t *)(e->d_misc + 2)); e->launches++;
         k_ss_cols<<<nt, TILE, 0, e->stream>>>(fmt.v, fmt.cf, e->ss_nplp, e->ss_fail, e->ss_extra, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
     }
@@ -1026,7 +1029,8 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     CK(cudaEventRecord(e->evB, e->stream));
     {
         MpEntFmt gf; gf.v = fmt.v; gf.cf = fmt.cf; gf.E = e->ent; gf.E2 = e->ent2;
-        k_mp_gather<<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        if (e->gather_occ == 8) k_mp_gather<8><<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        else k_mp_gather<6><<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
         e->launches++;
     }
     CK(cudaEventRecord(e->ev1, e->stream));

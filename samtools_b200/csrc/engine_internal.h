@@ -21,7 +21,7 @@ struct b200_engine {
     bool keep_raw = false, uploaded = false, has_host_clip = false;
     size_t qual_bytes = 0, n_cigar_total = 0;
     uint32_t smem_text = 24 * 1024;
-    int use_tma = 1, general = 0;
+    int use_tma = 1, general = 0, gather_occ = 6;
 
     // raw SoA image of the staged records
     DBUF(int64_t, pos); DBUF(uint16_t, flag); DBUF(uint8_t, mapq); DBUF(int32_t, l_qseq); DBUF(uint32_t, n_cigar);
