@@ -21,6 +21,7 @@
  *                         print_empty_pileup / -a gaps    bam_plcmd.c:372-398, :610-660, :880-910
  *   b200_depth_text()     add_depth + flush rows          bam2depth.c:209-477, zero_region :88-118
  *   b200_coverage()       column reducers                 coverage.c:589-661
+ *   b200_bedcov()         per-interval column reducers    bedcov.c:303-331
  *   b200_glf()            bcf_call_glfgen + errmod_cal    bam2bcf.c:65-123 (+ htslib errmod.c)
  *   b200_pileup_entries() bam_plp64_next/resolve_cigar2   (htslib sam.c) -> arrays of bam_pileup1_t fields
  *
@@ -186,6 +187,11 @@ int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *conf, char *out, 
 uint64_t b200_mpileup_text_bound(const b200_engine_t *e, const b200_mpileup_conf_t *conf);
 uint64_t b200_depth_text_bound(const b200_engine_t *e);
 int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *conf, b200_coverage_sums_t *sums);
+/* bedcov reducers (bedcov.c:316-331) over the staged window [beg,end): per input file the sum of the per-column depth --
+ * without deletions and reference skips when skip_del_refskip or min_depth >= 0, as the reference does -- and, for
+ * min_depth >= 0, the number of columns whose depth reaches it (pcov may be NULL).  Stage with B200_MODE_COVERAGE
+ * (rflag_filter = the -g/-G flag set, min_mq = -Q). */
+int b200_bedcov(b200_engine_t *e, int32_t skip_del_refskip, int32_t min_depth, uint64_t *cnt, uint64_t *pcov);
 /* genotype likelihoods per covered column and file: n, qsum[4], p[25].  col_pos == NULL: compute only, results stay in
  * HBM (device-only timing, like out == NULL of the text calls); *n_cols is then the number of candidate columns */
 int b200_glf(b200_engine_t *e, int32_t min_baseQ, int64_t *n_cols, int64_t *col_pos, int32_t *n_bases,

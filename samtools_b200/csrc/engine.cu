@@ -458,6 +458,39 @@ __global__ void __launch_bounds__(256) k_coverage(View v, int32_t min_baseQ, int
     }
 }
 
+// bedcov column reducers (bedcov.c:316-331) over the staged window, per input file: sum of the per-column depth (optionally
+// without deletions / reference skips) and the number of columns at or above a depth threshold.  A column takes part when
+// the multi-file iterator would return it, i.e. when any file has a read over it.
+__global__ void __launch_bounds__(256) k_bedcov(View v, int skip_dn, int min_depth, unsigned long long *sums /* [n_files][2] */)
+{
+    const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    const bool live = c < v.ncols;
+    bool any = false;
+    if (live)
+        for (int f = 0; f < v.n_files && !any; ++f) {
+            const ReadRange rr = read_range(v, f, c >> 5);
+            for (int32_t t_ = 0; t_ < rr.n && !any; ++t_) { const ReadDesc d = load_hot(v.desc + range_at(rr, t_)); any = (uint32_t)(c - d.rpos) < (uint32_t)(d.rend - d.rpos); }
+        }
+    for (int f = 0; f < v.n_files; ++f) {
+        unsigned long long pd = 0, ge = 0;
+        if (live && any) {
+            const ReadRange rr = read_range(v, f, c >> 5);
+            int32_t np = 0, m = 0;
+            for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+                const int32_t i = range_at(rr, t_);
+                ReadDesc d = load_hot(v.desc + i);
+                if ((uint32_t)(c - d.rpos) >= (uint32_t)(d.rend - d.rpos)) continue;
+                ++np;
+                if (skip_dn && !(d.fl & RD_SIMPLE)) { load_cold(d, v.desc + i); Ent e; resolve(v, d, c, e); if (e.is_del || e.is_refskip) ++m; }
+            }
+            pd = (unsigned long long)(np - m);
+            ge = (min_depth >= 0 && np - m >= min_depth) ? 1ull : 0ull;
+        }
+        for (int o = 16; o; o >>= 1) { pd += __shfl_xor_sync(0xffffffffu, pd, o); ge += __shfl_xor_sync(0xffffffffu, ge, o); }
+        if ((threadIdx.x & 31) == 0) { if (pd) atomicAdd(&sums[2 * f], pd); if (ge) atomicAdd(&sums[2 * f + 1], ge); }
+    }
+}
+
 // column-major pileup entries for the iterator tier: counts, then entries
 __global__ void k_entries_count(View v, int f, int32_t c0, uint32_t *col_n)   // columns [c0, v.ncols); col_n[c - c0]
 {
@@ -1086,6 +1119,28 @@ extern "C" int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b2
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
     sums->n_covered_bases = h[0]; sums->summed_coverage = h[1]; sums->summed_baseQ = h[2]; sums->quality_bases = h[3]; sums->missing_qual = h[4];
+    return 0;
+}
+
+extern "C" int b200_bedcov(b200_engine_t *e, int32_t skip_del_refskip, int32_t min_depth, uint64_t *cnt, uint64_t *pcov)
+{
+    if (!e || !e->staged) { if (e) snprintf(e->err, sizeof e->err, "no staged batch"); return -1; }
+    CK(cudaSetDevice(e->device));
+    View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);
+    const size_t nf = (size_t)e->n_files;
+    for (size_t f = 0; f < nf; ++f) { cnt[f] = 0; if (pcov) pcov[f] = 0; }
+    if (v.ncols <= 0) return 0;
+    ENSURE(col_off, 2 * nf + 2);
+    CK(cudaMemsetAsync(e->col_off, 0, 2 * nf * 8, e->stream));
+    CK(cudaEventRecord(e->ev0, e->stream));
+    k_bedcov<<<nblk(v.ncols, 256), 256, 0, e->stream>>>(v, (skip_del_refskip || min_depth >= 0) ? 1 : 0, min_depth, (unsigned long long *)e->col_off); e->launches++;
+    CK(cudaEventRecord(e->ev1, e->stream));
+    std::vector<uint64_t> h(2 * nf);
+    CK(cudaMemcpyAsync(h.data(), e->col_off, 2 * nf * 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
+    for (size_t f = 0; f < nf; ++f) { cnt[f] = h[2 * f]; if (pcov) pcov[f] = h[2 * f + 1]; }
     return 0;
 }
 

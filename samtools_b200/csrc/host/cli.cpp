@@ -1,4 +1,4 @@
-// cli.cpp -- `b200samtools mpileup|depth|coverage|gl`: the reference's CLI surface
+// cli.cpp -- `b200samtools mpileup|depth|coverage|bedcov|gl`: the reference's CLI surface
 // for the pileup hot path, driving the CUDA engine through its C ABI.
 //
 // Option surfaces follow bam_plcmd.c:1096-1223 (mpileup), bam2depth.c:757-882
@@ -15,6 +15,8 @@
 #include "hts_io.hpp"
 #include "packer.hpp"
 #include <getopt.h>
+#include <zlib.h>
+#include <cctype>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -36,6 +38,7 @@ struct FileData {
     std::vector<std::vector<Record>> by_tid;   // decoded records per reference sequence, file order (only the current one is populated)
     Record pending; bool have_pending = false, eof = false;
     int last_tid = -1;                          // reference sequence of the last mapped record seen (sortedness check)
+    bool keep_all = false;                      // bedcov: BED lines address the sequences in any order, keep everything
     int64_t n_no_tid = 0;
 };
 
@@ -57,7 +60,7 @@ bool load_file(const std::string &fn, const std::string &fai, const char *reg, F
 bool load_tid(FileData &fd, int tid, const char *cmd)
 {
     if (tid < 0 || tid >= (int)fd.by_tid.size()) return true;
-    for (int t = 0; t < tid; ++t) if (!fd.by_tid[(size_t)t].empty()) std::vector<Record>().swap(fd.by_tid[(size_t)t]);
+    if (!fd.keep_all) for (int t = 0; t < tid; ++t) if (!fd.by_tid[(size_t)t].empty()) std::vector<Record>().swap(fd.by_tid[(size_t)t]);
     std::vector<Record> &dst = fd.by_tid[(size_t)tid];
     for (;;) {
         if (!fd.have_pending) {
@@ -715,16 +718,134 @@ int main_coverage(int argc, char **argv)
     return 0;
 }
 
+// ----------------------------------------------------------------------------- bedcov
+// `samtools bedcov` (bedcov.c): for every BED line the reference opens an index query over [beg,end) and runs the
+// multi-file pileup iterator with the column reducers of bedcov.c:316-331.  Here every line stages the records that
+// overlap its interval (B200_MODE_COVERAGE read filters: the -g/-G flag set and -Q) and b200_bedcov() reduces the window
+// on the device.  BED lines may name the reference sequences in any order, so the inputs are decoded completely up front
+// (the reference has random access through the BAI; this driver has no index reader).
+int main_bedcov(int argc, char **argv)
+{
+    int c, min_mapQ = 0, skip_DN = 0, do_rcount = 0, min_depth = -1, max_depth = INT_MAX, print_header = 0, hdr = 0, status = 0, tflags;
+    int flags = F_UNMAP | F_SECONDARY | F_QCFAIL | F_DUP;
+    static const struct option lo[] = { {"min-MQ", 1, 0, 'Q'}, {"min-mq", 1, 0, 'Q'}, {"max-depth", 1, 0, 1000}, {0, 0, 0, 0} };
+    optind = 1;
+    while ((c = getopt_long(argc, argv, "Q:Xg:G:jd:Hc", lo, nullptr)) >= 0) {
+        switch (c) {
+        case 'Q': min_mapQ = atoi(optarg); break;
+        case 'X': break;
+        case 'c': do_rcount = 1; break;
+        case 'H': print_header = 1; break;
+        case 'g': tflags = parse_flag(optarg); if (tflags < 0 || tflags > 4095) { fprintf(stderr, "[bedcov] Flag value \"%s\" is not supported\n", optarg); return 1; } flags &= ~tflags; break;
+        case 'G': tflags = parse_flag(optarg); if (tflags < 0 || tflags > 4095) { fprintf(stderr, "[bedcov] Flag value \"%s\" is not supported\n", optarg); return 1; } flags |= tflags; break;
+        case 'j': skip_DN = 1; break;
+        case 'd': min_depth = atoi(optarg); break;
+        case 1000: max_depth = atoi(optarg); break;
+        default: fprintf(stderr, "Usage: samtools bedcov [options] <in.bed> <in1.bam> [...]\n"); return 1;
+        }
+    }
+    if (optind + 2 > argc) { fprintf(stderr, "Usage: samtools bedcov [options] <in.bed> <in1.bam> [...]\n"); return 1; }
+    const int n = argc - optind - 1;
+    char **fn = argv + optind + 1;
+    if (!print_header) hdr = 1;
+    std::vector<FileData> fd((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        int t = 0; int64_t b = 0, e = POS_MAX;
+        if (!load_file(fn[i], "", nullptr, fd[(size_t)i], t, b, e, "bedcov")) { fprintf(stderr, "ERROR: fail to open index BAM file '%s'\n", fn[i]); return 2; }
+        fd[(size_t)i].keep_all = true;
+        for (int tid = 0; tid < fd[(size_t)i].rd->header().n_ref(); ++tid) if (!load_tid(fd[(size_t)i], tid, "bedcov")) return 2;
+    }
+    const Header &h = fd[0].rd->header();
+    // per file and reference sequence: running maximum of the record ends, so that the first record that can reach an
+    // interval is found by binary search
+    std::vector<std::vector<std::vector<int64_t>>> runmax((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        runmax[(size_t)i].resize(fd[(size_t)i].by_tid.size());
+        for (size_t t = 0; t < fd[(size_t)i].by_tid.size(); ++t) {
+            int64_t m = INT64_MIN;
+            for (const Record &r : fd[(size_t)i].by_tid[t]) { m = std::max(m, r.endpos()); runmax[(size_t)i][t].push_back(m); }
+        }
+    }
+    gzFile fp = gzopen(argv[optind], "rb");
+    if (!fp) { fprintf(stderr, "[bedcov] can't open BED file '%s': %s\n", argv[optind], strerror(errno)); return 2; }
+    Engine eng;
+    if (!eng.init()) return 1;
+    b200_stage_conf_t sc; memset(&sc, 0, sizeof sc);
+    sc.mode = B200_MODE_COVERAGE; sc.rflag_filter = flags; sc.min_mq = min_mapQ; sc.max_depth = min_depth > max_depth ? min_depth : max_depth;
+    auto output_header = [&](const char *hline, int fields) {
+        static const char *bedcols[] = { "chrom", "chromStart", "chromEnd", "name", "score", "strand", "thickStart", "thickEnd", "itemRgb", "blockCount", "blockSizes", "blockStarts" };
+        if (hline) fputs(hline, stdout);
+        else for (int i = 0; i < fields; ++i) printf("%s%s", i ? "\t" : "#", i < 12 ? bedcols[i] : ".");
+        for (int i = 0; i < n; ++i) printf("\t%s_cov", fn[i]);
+        if (min_depth >= 0) for (int i = 0; i < n; ++i) printf("\t%s_depth", fn[i]);
+        if (do_rcount) for (int i = 0; i < n; ++i) printf("\t%s_count", fn[i]);
+        putchar('\n');
+    };
+    PackedBatch pb;
+    std::vector<uint64_t> cnt((size_t)n), pcov((size_t)n), rcnt((size_t)n);
+    std::vector<uint8_t> keep;
+    std::vector<char> line(1 << 16);
+    while (gzgets(fp, line.data(), (int)line.size())) {
+        size_t l = strlen(line.data());
+        while (l && (line[l - 1] == '\n' || line[l - 1] == '\r')) line[--l] = 0;
+        if (l == 0) continue;
+        if (line[0] == '#') { if (!hdr && !strncmp(line.data(), "#chrom", 6)) { output_header(line.data(), -1); hdr = 1; } continue; }
+        if (!strncmp(line.data(), "track ", 6) || !strncmp(line.data(), "browser ", 8)) continue;
+        if (!hdr) { int fields = 0; for (const char *t = line.data(); *t; ++t) if (*t == '\t') fields++; output_header(nullptr, fields + 1); hdr = 1; }
+        char *p = line.data();
+        while (*p && !isspace((unsigned char)*p)) ++p;
+        long long beg = 0, end = 0; int tid = -1;
+        bool ok = *p != 0;
+        if (ok) { const char sv = *p; *p = 0; tid = h.name2tid(line.data()); *p = sv; ok = tid >= 0; }
+        if (ok) ok = sscanf(p + 1, "%lld %lld", &beg, &end) >= 2 && end >= beg;
+        if (!ok) { fprintf(stderr, "Errors in BED line '%s'\n", line.data()); status = 2; continue; }
+        std::fill(cnt.begin(), cnt.end(), 0); std::fill(pcov.begin(), pcov.end(), 0); std::fill(rcnt.begin(), rcnt.end(), 0);
+        if (end > beg) {
+            pb.clear();
+            for (int i = 0; i < n; ++i) {
+                pb.begin_file();
+                if (tid >= (int)fd[(size_t)i].by_tid.size()) continue;
+                const std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
+                const std::vector<int64_t> &rm = runmax[(size_t)i][(size_t)tid];
+                size_t j = (size_t)(std::upper_bound(rm.begin(), rm.end(), (int64_t)beg) - rm.begin());   // first record whose running max end exceeds beg
+                for (; j < v.size() && v[j].pos < end; ++j) if (v[j].endpos() > beg) pb.add(v[j], 0, false);
+            }
+            pb.finish();
+            if (!pb.pos.empty()) {
+                b200_batch_t batch = pb.view(tid, h.lens[(size_t)tid], h.names[(size_t)tid], nullptr);
+                sc.beg = beg; sc.end = end;
+                b200_stage_stats_t st;
+                if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools bedcov: %s\n", b200_last_error(eng.e)); return 2; }
+                if (b200_bedcov(eng.e, skip_DN, min_depth, cnt.data(), pcov.data()) != 0) { fprintf(stderr, "samtools bedcov: %s\n", b200_last_error(eng.e)); return 2; }
+                if (do_rcount) {   // reads the iterator buffered (its constructor hook, bedcov.c:72-76): the kept reads of each file
+                    keep.resize(pb.pos.size());
+                    if (b200_fetch_mapq_keep(eng.e, nullptr, keep.data(), keep.size()) != 0) return 2;
+                    for (int i = 0; i < n; ++i) for (int64_t k = pb.file_start[(size_t)i]; k < pb.file_start[(size_t)i + 1]; ++k) if (keep[(size_t)k] == 2) rcnt[(size_t)i]++;
+                }
+            }
+        }
+        fputs(line.data(), stdout);
+        for (int i = 0; i < n; ++i) printf("\t%llu", (unsigned long long)cnt[(size_t)i]);
+        if (min_depth >= 0) for (int i = 0; i < n; ++i) printf("\t%llu", (unsigned long long)pcov[(size_t)i]);
+        if (do_rcount) for (int i = 0; i < n; ++i) printf("\t%llu", (unsigned long long)rcnt[(size_t)i]);
+        putchar('\n');
+    }
+    gzclose(fp);
+    fflush(stdout);
+    return status;
+}
+
 }  // namespace
 
 int main(int argc, char **argv)
 {
-    if (argc < 2) { fprintf(stderr, "Usage: b200samtools <mpileup|depth|coverage|gl> [options]\n"); return 1; }
+    if (argc < 2) { fprintf(stderr, "Usage: b200samtools <mpileup|depth|coverage|bedcov|gl> [options]\n"); return 1; }
     std::string cmd = argv[1];
     if (cmd == "mpileup") return main_mpileup(argc - 1, argv + 1, false);
     if (cmd == "gl") return main_mpileup(argc - 1, argv + 1, true);
     if (cmd == "depth") return main_depth(argc - 1, argv + 1);
     if (cmd == "coverage") return main_coverage(argc - 1, argv + 1);
+    if (cmd == "bedcov") return main_bedcov(argc - 1, argv + 1);
     fprintf(stderr, "b200samtools: unrecognized command '%s'\n", argv[1]);
     return 1;
 }

@@ -323,6 +323,28 @@ int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b200_coverage
     }
     return 0;
 }
+int b200_bedcov(b200_engine_t *e, int32_t skip_dn, int32_t min_depth, uint64_t *cnt, uint64_t *pcov)
+{
+    View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);
+    const bool dn = skip_dn || min_depth >= 0;
+    for (int f = 0; f < v.n_files; ++f) { cnt[f] = 0; if (pcov) pcov[f] = 0; }
+    for (int32_t c = 0; c < v.ncols; ++c) {
+        std::vector<int32_t> pd((size_t)v.n_files, 0); bool any = false;
+        for (int f = 0; f < v.n_files; ++f) {
+            const ReadRange rr = read_range(v, f, c >> 5);
+            for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+                const int32_t i = range_at(rr, t_);
+                const ReadDesc d = v.desc[i];
+                if (c < d.rpos || c >= d.rend) continue;
+                any = true; ++pd[(size_t)f];
+                if (dn) { Ent en; resolve(v, d, c, en); if (en.is_del || en.is_refskip) --pd[(size_t)f]; }
+            }
+        }
+        if (!any) continue;
+        for (int f = 0; f < v.n_files; ++f) { cnt[f] += (uint64_t)pd[(size_t)f]; if (pcov && min_depth >= 0 && pd[(size_t)f] >= min_depth) pcov[f]++; }
+    }
+    return 0;
+}
 int b200_glf(b200_engine_t *e, int32_t, int64_t *, int64_t *, int32_t *, float *, float *, size_t) { e->err = "emulation harness: GL not emulated"; return -1; }
 int b200_fetch_qual(b200_engine_t *e, uint8_t *q, size_t cap) { memcpy(q, e->qual.data(), std::min(cap, e->qual.size())); return 0; }
 int b200_fetch_mapq_keep(b200_engine_t *e, uint8_t *m, uint8_t *k, size_t n) { n = std::min(n, (size_t)e->b.n_reads); if (m) memcpy(m, e->mapq.data(), n); if (k) memcpy(k, e->state.data(), n); return 0; }

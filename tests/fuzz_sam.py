@@ -101,5 +101,7 @@ MPILEUP_OPTS = [
 DEPTH_OPTS = ['', '-a', '-aa', '-J', '-q 13', '-Q 20 -l 10', '-s', '-s -J -q 14', '-g 0x400', '-G 16', '--incl-flags 0x40', '--require-flags 0x3',
               '-r c0:50-400', '-a -r c1:1-100', '-b {bed}', '-aa -b {bed}', '-H']
 COVERAGE_OPTS = ['', '-q 20', '-Q 13', '--min-depth 2', '-l 20', '--ff 0', '--rf 0x10', '-r c0:50-400', '-r c1', '-H']
+# bedcov over x.bed (bedcov.c): -j / -d / -c / flag filters / header
+BEDCOV_OPTS = ['', '-j', '-d 2', '-c', '-H -d 1 -c', '-Q 20', '-g 0x400 -G 0x10', '-j -d 0']
 # genotype likelihoods (bcf_call_glfgen + errmod_cal per column and file); CUDA path only: the emulation harness has no GL
 GL_OPTS = ['-B', '-B -Q 0', '-B -x -A', '-B -q 20', '-B -r c0:50-400', '-B -6 -Q 0', '']

@@ -100,6 +100,15 @@ def all_cases():
              cmd="sed '/A1/d' sample.sam > sample1.sam; $samtools coverage --min-depth 1 sample.sam sample1.sam"),
         dict(id='testpl:coverage.5', cwd=d, kind='P', skip=None, table='test.pl', expected='test/coverage/5.expected',
              cmd="sed '/A1/d' sample.sam > sample1.sam; $samtools coverage --min-depth 4 sample.sam sample1.sam"),
+        # bedcov (test/test.pl:3817-3825): a further caller of the same pileup iterator (bedcov.c:303-331)
+        dict(id='testpl:bedcov', cwd='test/bedcov', kind='P', skip=None, table='test.pl', expected='test/bedcov/bedcov.expected',
+             cmd='$samtools bedcov bedcov.bed bedcov.bam'),
+        dict(id='testpl:bedcov_j', cwd='test/bedcov', kind='P', skip=None, table='test.pl', expected='test/bedcov/bedcov_j.expected',
+             cmd='$samtools bedcov -j bedcov.bed bedcov.bam'),
+        dict(id='testpl:bedcov_gG', cwd='test/bedcov', kind='P', skip=None, table='test.pl', expected='test/bedcov/bedcov_gG.expected',
+             cmd='$samtools bedcov -g512 -G2048 bedcov_gG.bed bedcov.bam'),
+        dict(id='testpl:bedcov_c', cwd='test/bedcov', kind='P', skip=None, table='test.pl', expected='test/bedcov/bedcov_c.expected',
+             cmd='$samtools bedcov -c bedcov_gG.bed bedcov.bam'),
         dict(id='testpl:large_pos.depth', cwd='test/large_pos', kind='P', skip=None, table='test.pl',
              expected='test/large_pos/depth.expected.out', cmd='$samtools depth longref.sam'),
         dict(id='testpl:large_pos.depth_bed', cwd='test/large_pos', kind='P', skip=None, table='test.pl',

@@ -23,9 +23,11 @@ def run_all(tool, oracle, td, seeds, need_noBAQ, with_gl=False):
         (d / 'x.sam').write_text(sam); (d / 'x.fa').write_text(fa)
         (d / 'x.bed').write_text('c0\t40\t300\nc0\t250\t600\nc1\t100\nc1\t95\t140\n')
         (d / 'rg.txt').write_text('g2\n')
+        (d / 'x3.bed').write_text('#chrom\tchromStart\tchromEnd\tname\nc0\t40\t300\ta\nc1\t95\t140\tb\nc0\t250\t600\tc\nc0\t10\t10\td\nc1\t0\t2000\te\n')
         (d / 'x2.sam').write_text(fuzz_sam.make_sam(seed + 100000, n_reads=25)[0])
         cases = [('mpileup', o) for o in fuzz_sam.MPILEUP_OPTS] + [('depth', o) for o in fuzz_sam.DEPTH_OPTS] + \
                 [('coverage', o) for o in fuzz_sam.COVERAGE_OPTS]
+        cases += [('bedcov', o) for o in fuzz_sam.BEDCOV_OPTS]
         if with_gl:
             cases += [('gl', o) for o in fuzz_sam.GL_OPTS]
         for cmd, opt in cases:
@@ -36,6 +38,8 @@ def run_all(tool, oracle, td, seeds, need_noBAQ, with_gl=False):
             opt = opt.format(bed='x.bed', rg='rg.txt')
             files = 'x.sam x2.sam' if (seed % 3 == 0 and '-r' not in opt) else 'x.sam'
             ref = '-f x.fa' if cmd in ('mpileup', 'gl') and seed % 4 != 1 else ''
+            if cmd == 'bedcov':
+                files = 'x3.bed ' + files
             tasks.append((seed, f'{cmd} {opt} {ref} {files}', d))
 
     def one(t):
