@@ -139,6 +139,12 @@ typedef struct {
                                 (QNAME/extras): only their "\t*" placeholders on empty rows */
     /* per-column BED filter (-l): sorted, non-overlapping-start intervals of this tid */
     const int64_t *bed_beg, *bed_end; int32_t n_bed; int32_t bed_active;
+    /* host columns ON the device (--output-QNAME, --output-extra fields and tags; bam_plcmd.c:727-855): the caller renders,
+     * per read of the staged batch, the string each column prints for it (a decimal FLAG, the QNAME, a tag value or the
+     * --output-empty character ...) and the device gathers them per pileup column, in file order, for the reads that pass
+     * -Q, joined by x_sep[k].  n_x (<= 16) must equal n_star_cols; column k of read i is
+     * x_dat[x_off[k * (n_reads + 1) + i] .. x_off[k * (n_reads + 1) + i + 1]).  n_x = 0: place holders only. */
+    int32_t n_x; const uint32_t *x_off; const char *x_dat; uint64_t x_bytes; char x_sep[16];
 } b200_mpileup_conf_t;
 
 typedef struct {

@@ -951,6 +951,7 @@ static void fill_view(b200_engine *e, View &v, const int64_t *bed_beg, const int
     v.ncols = (int32_t)(all ? std::max(e->ncols_cov, e->ncols_all) : e->ncols_cov);
     v.name = e->dname; v.name_len = (int32_t)e->name.size();
     v.bed_beg = bed_beg; v.bed_end = bed_end; v.n_bed = n_bed; v.bed_active = bed_active;
+    v.n_x = 0; v.x_stride = 0; v.x_off = nullptr; v.x_dat = nullptr; memset(v.x_sep, 0, sizeof v.x_sep);
 }
 
 static int upload_bed(b200_engine *e, const int64_t *bb, const int64_t *be, int n, int active)
@@ -1008,7 +1009,17 @@ static int run_text(b200_engine *e, KS k_size, KW k_write, const Fmt &fmt, uint6
 static uint64_t mpileup_bound(const b200_engine *e, const b200_mpileup_conf_t *c)
 {
     const int per = 2 + (c->out_mapq ? 1 : 0) + (c->out_qpos ? 12 : 0) + (c->out_qpos5 ? 13 : 0);
-    return e->text_bound(per, 1 + 2 * (3 + c->n_star_cols));
+    uint64_t b = e->text_bound(per, 1 + 2 * (3 + c->n_star_cols));
+    if (c->n_x > 0 && c->x_off) {   // host columns: every (read, column) entry can add the read's strings + separators
+        uint64_t worst = 0;
+        for (int64_t i = 0; i < e->n; ++i) {
+            uint64_t w = 0;
+            for (int k = 0; k < c->n_x; ++k) { const uint32_t *o = c->x_off + (size_t)k * ((size_t)e->n + 1) + (size_t)i; w += (uint64_t)(o[1] - o[0]) + 1; }
+            worst = std::max(worst, w);
+        }
+        b += (uint64_t)e->sum_rlen * worst;
+    }
+    return b;
 }
 extern "C" uint64_t b200_mpileup_text_bound(const b200_engine_t *e, const b200_mpileup_conf_t *c) { return (e && e->staged && c) ? mpileup_bound(e, c) : 0; }
 
@@ -1023,7 +1034,13 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     fmt.cf.no_del = c->no_del; fmt.cf.no_ends = c->no_ends; fmt.cf.out_mapq = c->out_mapq; fmt.cf.out_qpos = c->out_qpos;
     fmt.cf.out_qpos5 = c->out_qpos5; fmt.cf.n_star_cols = c->n_star_cols;
     const uint64_t bound = mpileup_bound(e, c);
-    if (e->general || e->n_files != 1 || c->out_qpos || c->out_qpos5)
+    if (c->n_x > 0) {   // host columns: upload the per-read string tables, widen the bound by the longest per-read contribution
+        if (c->n_x > PLP_MAX_X || c->n_x != c->n_star_cols || !c->x_off || (!c->x_dat && c->x_bytes)) { snprintf(e->err, sizeof e->err, "bad host-column tables"); return -1; }
+        const size_t n_off = (size_t)c->n_x * ((size_t)e->n + 1);
+        H2D(x_off, c->x_off, n_off); H2D(x_dat, c->x_dat, c->x_bytes ? c->x_bytes : 1);
+        fmt.v.n_x = c->n_x; fmt.v.x_stride = e->n + 1; fmt.v.x_off = e->x_off; fmt.v.x_dat = e->x_dat; memcpy(fmt.v.x_sep, c->x_sep, sizeof fmt.v.x_sep);
+    }
+    if (e->general || e->n_files != 1 || c->out_qpos || c->out_qpos5 || c->n_x > 0)
         return run_text(e, k_mpileup_size, k_mpileup_write, fmt, bound, out, out_cap, out_len);
     // ---- default (one input file, no -O columns): entry strings + gather (mpileup_ent.cuh)
     const int32_t ncols = fmt.v.ncols;

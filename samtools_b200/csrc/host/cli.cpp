@@ -155,6 +155,10 @@ struct MpOpts {
     std::unique_ptr<Fasta> fa; std::unique_ptr<Bed> bed;
     std::set<std::string> rg_excl; bool have_rg = false;
     bool gl = false;
+    // host columns (bam_plcmd.c:727-855): record fields in the order of the MPLP_PRINT_* bits, then aux tags in the order given
+    std::vector<std::string> xcols;      // "QNAME" "FLAG" "RNAME" "POS" "MAPQ" "RNEXT" "PNEXT" "RLEN" or a two-letter tag
+    int n_xfields = 0;                   // how many of them are record fields (joined with ','; tags use x_sep)
+    char x_sep = ',', x_empty = '*';
 };
 
 int count_samples(const std::vector<std::string> &fn, const std::vector<FileData> &fd, bool ignore_rg)
@@ -247,16 +251,65 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
     const int nref = h.n_ref();
     std::vector<size_t> sel; std::vector<size_t> cursor((size_t)nfn);
     std::vector<std::vector<uint8_t>> hbits((size_t)nfn);   // host bits of the contig's records, decided ONCE (the BQ:Z path edits the record)
+    std::vector<const Record *> staged;                     // records of the staged window, batch order (host columns)
+    std::vector<uint32_t> x_off; std::string x_dat; std::vector<uint8_t> x_mapq;
+    // per-read strings of the host columns (--output-QNAME / --output-extra, bam_plcmd.c:727-855) for the staged window
+    auto render_host_columns = [&]() -> int {
+        const size_t nr = staged.size(), nx = o.xcols.size();
+        x_off.assign(nx * (nr + 1), 0); x_dat.clear();
+        bool need_mapq = false;
+        for (const std::string &cname : o.xcols) if (cname == "MAPQ") need_mapq = true;
+        if (need_mapq && nr) { x_mapq.resize(nr); if (b200_fetch_mapq_keep(eng.e, x_mapq.data(), nullptr, nr) != 0) return -1; }   // after -C
+        char tmp[64];
+        for (size_t k = 0; k < nx; ++k) {
+            const std::string &cname = o.xcols[k];
+            const bool is_tag = (int)k >= o.n_xfields;
+            for (size_t i = 0; i < nr; ++i) {
+                const Record &r = *staged[i];
+                x_off[k * (nr + 1) + i] = (uint32_t)x_dat.size();
+                if (!is_tag) {
+                    if (cname == "QNAME") x_dat += r.qname;
+                    else if (cname == "FLAG") { snprintf(tmp, sizeof tmp, "%d", (int)r.flag); x_dat += tmp; }
+                    else if (cname == "RNAME") x_dat += r.tid >= 0 ? h.names[(size_t)r.tid] : std::string("*");
+                    else if (cname == "POS") { snprintf(tmp, sizeof tmp, "%lld", (long long)r.pos + 1); x_dat += tmp; }
+                    else if (cname == "MAPQ") { snprintf(tmp, sizeof tmp, "%d", (int)x_mapq[i]); x_dat += tmp; }
+                    else if (cname == "RNEXT") x_dat += (r.mtid >= 0 && r.mtid < h.n_ref()) ? h.names[(size_t)r.mtid] : std::string("*");
+                    else if (cname == "PNEXT") { snprintf(tmp, sizeof tmp, "%lld", (long long)r.mpos + 1); x_dat += tmp; }
+                    else if (cname == "RLEN") { snprintf(tmp, sizeof tmp, "%d", (int)r.l_qseq); x_dat += tmp; }
+                } else {
+                    const uint8_t *t = r.aux_get(cname.c_str());
+                    if (!t) x_dat += o.x_empty;
+                    else switch (*t) {
+                        case 'Z': case 'H': x_dat += (const char *)t + 1; break;
+                        case 'c': snprintf(tmp, sizeof tmp, "%d", (int)(int8_t)t[1]); x_dat += tmp; break;
+                        case 'C': snprintf(tmp, sizeof tmp, "%d", (int)t[1]); x_dat += tmp; break;
+                        case 's': { int16_t v; memcpy(&v, t + 1, 2); snprintf(tmp, sizeof tmp, "%d", (int)v); x_dat += tmp; break; }
+                        case 'S': { uint16_t v; memcpy(&v, t + 1, 2); snprintf(tmp, sizeof tmp, "%d", (int)v); x_dat += tmp; break; }
+                        case 'i': { int32_t v; memcpy(&v, t + 1, 4); snprintf(tmp, sizeof tmp, "%d", v); x_dat += tmp; break; }
+                        case 'I': { uint32_t v; memcpy(&v, t + 1, 4); snprintf(tmp, sizeof tmp, "%u", v); x_dat += tmp; break; }
+                        case 'f': { float v; memcpy(&v, t + 1, 4); snprintf(tmp, sizeof tmp, "%g", (double)v); x_dat += tmp; break; }
+                        case 'd': { double v; memcpy(&v, t + 1, 8); snprintf(tmp, sizeof tmp, "%g", v); x_dat += tmp; break; }
+                        case 'A': x_dat += (char)t[1]; break;
+                        default: x_dat += '*'; break;
+                    }
+                }
+            }
+            x_off[k * (nr + 1) + nr] = (uint32_t)x_dat.size();
+        }
+        mc.n_x = (int32_t)nx; mc.n_star_cols = (int32_t)nx; mc.x_off = x_off.data(); mc.x_dat = x_dat.data(); mc.x_bytes = x_dat.size();
+        for (size_t k = 0; k < nx; ++k) mc.x_sep[k] = (int)k < o.n_xfields ? ',' : o.x_sep;
+        return 0;
+    };
     // one window [wb,we) of contig tid: stage the overlapping records, return the stage statistics
     auto stage_window = [&](int tid, bool with_reads, int64_t wb, int64_t we, const std::string *ref, b200_stage_stats_t &st) -> int {
         const std::string &name = h.names[(size_t)tid];
-        pb.clear();
+        pb.clear(); staged.clear();
         for (int i = 0; i < nfn; ++i) {
             pb.begin_file();
             if (with_reads && tid < (int)fd[(size_t)i].by_tid.size()) {
                 std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
                 window_records(v, cursor[(size_t)i], wb, we, sel);
-                for (size_t j : sel) pb.add(v[j], hbits[(size_t)i][j], o.overlaps);
+                for (size_t j : sel) { pb.add(v[j], hbits[(size_t)i][j], o.overlaps); if (!o.xcols.empty()) staged.push_back(&v[j]); }
             }
         }
         pb.finish();
@@ -320,6 +373,7 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
                 }
                 continue;
             }
+            if (!o.xcols.empty() && render_host_columns() != 0) { fprintf(stderr, "samtools mpileup: %s\n", b200_last_error(eng.e)); return -1; }
             const size_t bound = (size_t)b200_mpileup_text_bound(eng.e, &mc);
             if (out.size() < bound + 64) out.resize(bound + 64);
             size_t need = 0;
@@ -363,6 +417,7 @@ int main_mpileup(int argc, char **argv, bool gl)
 {
     MpOpts o; o.gl = gl;
     const char *file_list = nullptr; bool use_orphan = false, has_index_file = false;
+    int want_fields = 0; std::vector<std::string> want_tags;
     static const struct option lo[] = {
         {"rf", 1, 0, 1}, {"ff", 1, 0, 2}, {"incl-flags", 1, 0, 1}, {"excl-flags", 1, 0, 2}, {"output", 1, 0, 3},
         {"output-QNAME", 0, 0, 5}, {"output-qname", 0, 0, 5}, {"illumina1.3+", 0, 0, '6'}, {"count-orphans", 0, 0, 'A'},
@@ -383,11 +438,30 @@ int main_mpileup(int argc, char **argv, bool gl)
         case 1: o.rf = parse_flag(optarg); if (o.rf < 0) { fprintf(stderr, "Could not parse --rf %s\n", optarg); return 1; } break;
         case 2: o.ff = parse_flag(optarg); if (o.ff < 0) { fprintf(stderr, "Could not parse --ff %s\n", optarg); return 1; } break;
         case 3: case 'o': o.out_fn = optarg; break;
-        case 5: case 7: case 'M':
-            fprintf(stderr, "b200samtools mpileup: --output-QNAME/--output-extra/--output-mods are not available on the device path yet\n");
+        case 'M':
+            fprintf(stderr, "b200samtools mpileup: --output-mods is not available on the device path yet\n");
             return 1;
+        case 5: want_fields |= 1 << 0; break;                      // --output-QNAME
+        case 7: {                                                  // --output-extra FLAG,QNAME,TAG,...   (bam_plcmd.c:1013-1067)
+            static const char *names[] = { "QNAME", "FLAG", "RNAME", "POS", "MAPQ", "RNEXT", "PNEXT", "RLEN" };
+            std::string a = optarg; size_t st = 0;
+            while (st <= a.size()) {
+                size_t e2 = a.find(',', st); if (e2 == std::string::npos) e2 = a.size();
+                const std::string t = a.substr(st, e2 - st);
+                int fld = -1;
+                for (int k = 0; k < 8; ++k) if (t == names[k]) fld = k;
+                if (fld >= 0) want_fields |= 1 << fld;
+                else if (t.size() == 2) { if (std::find(want_tags.begin(), want_tags.end(), t) == want_tags.end()) want_tags.push_back(t); }
+                else if (t == "MAPQ" || t.empty()) {}
+                else { fprintf(stderr, "[mpileup] unknown field or bad tag name in --output-extra: \"%s\"\n", t.c_str()); return 1; }
+                st = e2 + 1;
+            }
+            break;
+        }
         case 6: o.rev_del = 1; break;
-        case 8: case 9: case 11: break;
+        case 8: o.x_sep = optarg[0]; break;                      // --output-sep
+        case 9: o.x_empty = optarg[0]; break;                    // --output-empty
+        case 11: break;
         case 10: o.no_ins++; break;
         case 12: o.no_del++; break;
         case 13: o.no_ends = 1; break;
@@ -420,6 +494,14 @@ int main_mpileup(int argc, char **argv, bool gl)
     }
     if (!o.realn && o.redo_baq) { fprintf(stderr, "Error: The -B option cannot be combined with -E\n"); return 1; }
     if (use_orphan) o.no_orphan = false;
+    {   // record fields print in the order of the MPLP_PRINT_* bits (bam_plcmd.c:185-196,728-795), tags after them in the order given
+        static const char *names[] = { "QNAME", "FLAG", "RNAME", "POS", "MAPQ", "RNEXT", "PNEXT", "RLEN" };
+        for (int k = 0; k < 8; ++k) if (want_fields & (1 << k)) o.xcols.push_back(names[k]);
+        o.n_xfields = (int)o.xcols.size();
+        for (const std::string &t : want_tags) o.xcols.push_back(t);
+        if (o.xcols.size() > 16) { fprintf(stderr, "b200samtools mpileup: at most 16 --output-extra columns\n"); return 1; }
+        if (o.n_xfields && o.out_qpos5) { fprintf(stderr, "b200samtools mpileup: --output-BP-5 together with --output-QNAME/--output-extra fields is not available on the device path\n"); return 1; }
+    }
     if (argc == 1) { fprintf(stderr, "\nUsage: samtools mpileup [options] in1.bam [in2.bam [...]]\n"); return 1; }
     std::vector<std::string> fn;
     if (file_list) {

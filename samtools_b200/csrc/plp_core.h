@@ -123,7 +123,12 @@ struct View {
     int32_t ncols_all;         // -a: columns [0,ncols_all) are emitted even if empty
     const char *name; int32_t name_len;
     const int64_t *bed_beg, *bed_end; int32_t n_bed; int32_t bed_active;
+    // per-read strings of the host columns (--output-QNAME, --output-extra fields and tags; bam_plcmd.c:727-855): column k
+    // of read i is x_dat[x_off[k * (n_reads + 1) + i] .. x_off[k * (n_reads + 1) + i + 1]); entries of one pileup column
+    // are joined with x_sep[k].  n_x == 0: none (then MpConf::n_star_cols only produces "*" place holders)
+    int32_t n_x; int64_t x_stride; const uint32_t *x_off; const char *x_dat; char x_sep[16];
 };
+constexpr int PLP_MAX_X = 16;
 
 // Reads that can cover a 32-column group = far-reaching reads (index < lo, e.g. spliced or
 // long-deletion alignments; usually none) followed by the contiguous slice [lo,hi).  Both parts
@@ -402,6 +407,62 @@ PLP_HD int32_t qpos5_of(const ReadDesc &d, const Ent &e)
     return (d.fl & RD_REV) ? d.l_qseq - e.qpos + (int)e.is_del : e.qpos + 1;
 }
 
+// quality the reference tests against -Q for read d at column c (simple reads without the cursor)
+PLP_HD int col_qual(const View &v, const ReadDesc &d, int32_t i, int32_t c)
+{
+    if (d.fl & RD_SIMPLE) return (int)v.qual[d.qoff + (uint32_t)d.qstart + (uint32_t)(c - d.rpos)];
+    ReadDesc dd = d; load_cold(dd, v.desc + i);
+    Ent e; resolve(v, dd, c, e);
+    return ent_qual(v, dd, e);
+}
+// bytes of every host column of file f at column c (contents only: strings of the reads that pass -Q plus separators)
+PLP_HD void mp_x_sizes(const View &v, const MpConf &cf, int f, int tile, int32_t c, uint32_t *xl)
+{
+    for (int k = 0; k < v.n_x; ++k) xl[k] = 0;
+    const ReadRange rr = read_range(v, f, tile);
+    int n = 0;
+    for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+        const int32_t i = range_at(rr, t_);
+        const ReadDesc d = load_hot(v.desc + i);
+        if ((uint32_t)(c - d.rpos) >= (uint32_t)(d.rend - d.rpos)) continue;
+        if (col_qual(v, d, i, c) < cf.min_baseQ) continue;
+        for (int k = 0; k < v.n_x; ++k) { const uint32_t *o = v.x_off + (int64_t)k * v.x_stride + i; xl[k] += (o[1] - o[0]) + (n ? 1u : 0u); }
+        ++n;
+    }
+}
+PLP_HD uint32_t mp_x_section_len(const View &v, const MpConf &cf, int f, int tile, int32_t c, const MpFileSz &s)
+{
+    if (!v.n_x || s.nplp == 0 || s.cnt == 0) return 0;     // the "\t*" place holders are already in mp_file_section_len
+    uint32_t xl[PLP_MAX_X];
+    mp_x_sizes(v, cf, f, tile, c, xl);
+    uint32_t n = 0;
+    for (int k = 0; k < v.n_x; ++k) n += xl[k];
+    return n - (uint32_t)v.n_x;                            // instead of the one-byte "*" of each column
+}
+// the host columns of file f at column c, written at p (which points just behind the last device column)
+PLP_HD char *mp_x_write(const View &v, const MpConf &cf, int f, int tile, int32_t c, char *p)
+{
+    uint32_t xl[PLP_MAX_X];
+    mp_x_sizes(v, cf, f, tile, c, xl);
+    char *px[PLP_MAX_X];
+    for (int k = 0; k < v.n_x; ++k) { *p++ = '\t'; px[k] = p; p += xl[k]; }
+    const ReadRange rr = read_range(v, f, tile);
+    int n = 0;
+    for (int32_t t_ = 0; t_ < rr.n; ++t_) {
+        const int32_t i = range_at(rr, t_);
+        const ReadDesc d = load_hot(v.desc + i);
+        if ((uint32_t)(c - d.rpos) >= (uint32_t)(d.rend - d.rpos)) continue;
+        if (col_qual(v, d, i, c) < cf.min_baseQ) continue;
+        for (int k = 0; k < v.n_x; ++k) {
+            const uint32_t *o = v.x_off + (int64_t)k * v.x_stride + i;
+            if (n) *px[k]++ = v.x_sep[k];
+            for (uint32_t j = o[0]; j < o[1]; ++j) *px[k]++ = v.x_dat[j];
+        }
+        ++n;
+    }
+    return p;
+}
+
 PLP_HD void mp_file_size(const View &v, const MpConf &cf, int f, int tile, int32_t c, MpFileSz &s)
 {
     s.nplp = 0; s.cnt = 0; s.seq_len = 0; s.bp_len = 0; s.bp5_len = 0;
@@ -581,6 +642,7 @@ PLP_HD char *mp_file_write(const View &v, const MpConf &cf, int f, int tile, int
     pq = p + (s.seq_len ? s.seq_len : 1);
     *pq = '\t';
     p = pend;
+    if (v.n_x && s.cnt) return mp_x_write(v, cf, f, tile, c, p);
     for (int i = 0; i < cf.n_star_cols; ++i) { *p++ = '\t'; *p++ = '*'; }
     return p;
 }
@@ -609,7 +671,7 @@ PLP_HD uint32_t mp_line_size(const View &v, const MpConf &cf, int tile, int32_t 
         mp_file_size(v, cf, f, tile, c, s);
         if (f == 0) s0 = s;
         any |= s.nplp > 0;
-        body += mp_file_section_len(cf, s);
+        body += mp_file_section_len(cf, s) + mp_x_section_len(v, cf, f, tile, c, s);
     }
     if (!any && !(cf.all && c < v.ncols_all)) return 0;
     if (!bed_pass(v, c)) return 0;

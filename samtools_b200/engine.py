@@ -48,7 +48,8 @@ class StageStats(C.Structure):
 class MpileupConf(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('min_baseQ', 'all', 'rev_del', 'no_ins', 'no_del', 'no_ends', 'out_mapq', 'out_qpos',
                                           'out_qpos5', 'n_star_cols')] + \
-               [('bed_beg', C.c_void_p), ('bed_end', C.c_void_p), ('n_bed', C.c_int32), ('bed_active', C.c_int32)]
+               [('bed_beg', C.c_void_p), ('bed_end', C.c_void_p), ('n_bed', C.c_int32), ('bed_active', C.c_int32)] + \
+               [('n_x', C.c_int32), ('x_off', C.c_void_p), ('x_dat', C.c_void_p), ('x_bytes', C.c_uint64), ('x_sep', C.c_char * 16)]
 
 
 class DepthConf(C.Structure):

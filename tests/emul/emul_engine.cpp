@@ -206,6 +206,7 @@ static void fill_view(b200_engine *e, View &v, const int64_t *bb, const int64_t 
     v.ncols = (int32_t)(all ? std::max(e->ncols_cov, e->ncols_all) : e->ncols_cov);
     v.name = e->name.c_str(); v.name_len = (int32_t)e->name.size();
     v.bed_beg = bb; v.bed_end = be; v.n_bed = nb; v.bed_active = active;
+    v.n_x = 0; v.x_stride = 0; v.x_off = nullptr; v.x_dat = nullptr; memset(v.x_sep, 0, sizeof v.x_sep);
 }
 
 static int emit(b200_engine *e, const std::string &s, char *out, size_t cap, size_t *out_len)
@@ -224,7 +225,8 @@ int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out,
     // walk over the same per-base functions), the order-free line sizes, then mp_line_write_ent per column.
     // EMUL_GENERAL=1 replays the general path (mp_line_size + mp_line_write) like B200_PLP_GENERAL=1 on the device.
     const char *gen = getenv("EMUL_GENERAL");
-    const bool use_ent = !(gen && atoi(gen) == 1) && v.n_files == 1 && !cf.out_qpos && !cf.out_qpos5;
+    if (c->n_x > 0) { v.n_x = c->n_x; v.x_stride = e->b.n_reads + 1; v.x_off = c->x_off; v.x_dat = c->x_dat; memcpy(v.x_sep, c->x_sep, sizeof v.x_sep); }
+    const bool use_ent = !(gen && atoi(gen) == 1) && v.n_files == 1 && !cf.out_qpos && !cf.out_qpos5 && c->n_x == 0;
     std::vector<uint16_t> E, E2; std::vector<int32_t> diff; std::vector<uint32_t> fail, extra;
     if (use_ent) {
         const uint8_t *tab = (const uint8_t *)".ACMGRSVTWYHKDBN,acmgrsvtwyhkdbn";

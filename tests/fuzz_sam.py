@@ -97,6 +97,7 @@ MPILEUP_OPTS = [
     '-B --reverse-del --no-output-ends -Q 0', '-B --no-output-ins --no-output-del', '-B --no-output-ins --no-output-ins --no-output-del --no-output-del',
     '-B --rf 0x10', '-B --ff 0x400 -A', '-B -r c0:50-400', '-B -aa -r c1:90-130', '-B -a -r c0:100-101', '-B -6 -Q 0', '-B -l {bed}', '-B -a -l {bed}',
     '-B -G {rg}', '-B -R', '-B -C 50', '', '-E', '-x', '-a -Q 0', '-6 -A', '-r c1:1-200 -A -Q 5',
+    '-B --output-QNAME -a', "-B -s -O --output-extra FLAG,QNAME,RG,NM,POS,MAPQ,RNEXT,PNEXT,RLEN,RNAME --output-sep ';' --output-empty -",
 ]
 DEPTH_OPTS = ['', '-a', '-aa', '-J', '-q 13', '-Q 20 -l 10', '-s', '-s -J -q 14', '-g 0x400', '-G 16', '--incl-flags 0x40', '--require-flags 0x3',
               '-r c0:50-400', '-a -r c1:1-100', '-b {bed}', '-aa -b {bed}', '-H']
