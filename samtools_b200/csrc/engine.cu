@@ -131,33 +131,39 @@ __device__ __forceinline__ unsigned long long warp_sum_u48(unsigned long long v)
     const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(v >> 32));
     return (unsigned long long)lo + ((unsigned long long)mid << 16) + ((unsigned long long)hi << 32);
 }
+// Block-wide merge of the per-thread accumulators: warp reductions (single-instruction redux.sync; per-lane values are tiny:
+// a read contributes 0/1 to the counters, its span / text bound / mapq to the sums), then the block's warps through shared
+// memory, then ONE set of atomics per block.  The kernels that call this are grid-stride with a few blocks per SM, so a
+// stage issues ~10^4 same-address atomics instead of one set per warp (3*10^5 for 1.6 M reads: they serialise in L2 and
+// were most of k_build_desc's 0.18 ms).  Must be called by every thread of the block.
 __device__ __forceinline__ void merge_acc(const StageAcc &a, StageAcc *g)
 {
-    // per-lane values are tiny (a read contributes 0/1 to the counters, its span / text bound / mapq to the sums):
-    // single-instruction warp reductions instead of 64-bit shuffle trees (the trees cost ~180 issue slots per warp)
-    const unsigned n_kept = __reduce_add_sync(0xffffffffu, (unsigned)a.n_kept), n_win = __reduce_add_sync(0xffffffffu, (unsigned)a.n_kept_in_window);
-    const unsigned n_reads = __reduce_add_sync(0xffffffffu, (unsigned)a.n_reads), n_sel = __reduce_add_sync(0xffffffffu, (unsigned)a.n_selected);
-    const unsigned mq = __reduce_add_sync(0xffffffffu, (unsigned)a.summed_mapq), n_desc = __reduce_add_sync(0xffffffffu, (unsigned)a.n_desc);
-    const unsigned long long rl = warp_sum_u48(a.sum_rlen), it = warp_sum_u48(a.sum_indel_text), rg = warp_sum_u48(a.sum_rlen_gen);
+    __shared__ unsigned long long s_v[32][9];
+    __shared__ int s_mx[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    unsigned long long v[9];
+    v[0] = __reduce_add_sync(0xffffffffu, (unsigned)a.n_kept); v[1] = __reduce_add_sync(0xffffffffu, (unsigned)a.n_kept_in_window);
+    v[2] = warp_sum_u48(a.sum_rlen); v[3] = warp_sum_u48(a.sum_indel_text);
+    v[4] = __reduce_add_sync(0xffffffffu, (unsigned)a.n_reads); v[5] = __reduce_add_sync(0xffffffffu, (unsigned)a.n_selected);
+    v[6] = warp_sum_u48(a.summed_mapq); v[7] = __reduce_add_sync(0xffffffffu, (unsigned)a.n_desc); v[8] = warp_sum_u48(a.sum_rlen_gen);
     const int mx = __reduce_max_sync(0xffffffffu, a.max_rend);
-    if ((threadIdx.x & 31) == 0) {
-        if (n_kept) atomicAdd(&g->n_kept, (unsigned long long)n_kept);
-        if (n_win) atomicAdd(&g->n_kept_in_window, (unsigned long long)n_win);
-        if (rl) atomicAdd(&g->sum_rlen, rl);
-        if (it) atomicAdd(&g->sum_indel_text, it);
-        if (n_reads) atomicAdd(&g->n_reads, (unsigned long long)n_reads);
-        if (n_sel) atomicAdd(&g->n_selected, (unsigned long long)n_sel);
-        if (mq) atomicAdd(&g->summed_mapq, (unsigned long long)mq);
-        if (n_desc) atomicAdd(&g->n_desc, (unsigned long long)n_desc);
-        if (rg) atomicAdd(&g->sum_rlen_gen, rg);
-        if (mx != INT32_MIN) atomicMax(&g->max_rend, mx);
+    if (lane == 0) { for (int k = 0; k < 9; ++k) s_v[w][k] = v[k]; s_mx[w] = mx; }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        unsigned long long t = 0;
+        for (int j = 0; j < nw; ++j) t += s_v[j][threadIdx.x];
+        unsigned long long *gp[9] = {&g->n_kept, &g->n_kept_in_window, &g->sum_rlen, &g->sum_indel_text, &g->n_reads, &g->n_selected, &g->summed_mapq, &g->n_desc, &g->sum_rlen_gen};
+        if (t) atomicAdd(gp[threadIdx.x], t);
+    } else if (threadIdx.x == 32) {
+        int m = INT32_MIN;
+        for (int j = 0; j < nw; ++j) m = max(m, s_mx[j]);
+        if (m != INT32_MIN) atomicMax(&g->max_rend, m);
     }
 }
 __global__ void k_prep1(RawSoA r, b200_stage_conf_t cf, uint8_t *state, int32_t *rlen_out, StageAcc *acc)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     StageAcc loc; memset(&loc, 0, sizeof loc); loc.max_rend = INT32_MIN;
-    if (i < r.n) stage_prep1(r, cf, i, state, rlen_out, &loc);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += (int64_t)gridDim.x * blockDim.x) stage_prep1(r, cf, i, state, rlen_out, &loc);
     if (cf.mode == B200_MODE_COVERAGE) merge_acc(loc, acc);
 }
 __global__ void k_prep2(RawSoA r, b200_stage_conf_t cf, uint8_t *state)
@@ -168,9 +174,9 @@ __global__ void k_prep2(RawSoA r, b200_stage_conf_t cf, uint8_t *state)
 __global__ void k_build_desc(RawSoA r, b200_stage_conf_t cf, const uint8_t *state, const int32_t *rlen,
                              ReadDesc *desc, int32_t *endv, StageAcc *acc, int64_t win_base, int32_t *cig_x, int32_t *cig_y)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     StageAcc loc; memset(&loc, 0, sizeof loc); loc.max_rend = INT32_MIN;
-    if (i < r.n) stage_build_desc(r, cf, i, state, rlen, desc, endv, &loc, win_base, cig_x, cig_y);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += (int64_t)gridDim.x * blockDim.x)
+        stage_build_desc(r, cf, i, state, rlen, desc, endv, &loc, win_base, cig_x, cig_y);
     merge_acc(loc, acc);
 }
 
@@ -609,11 +615,10 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     e->smem_text = 24 * 1024;
     const char *s = getenv("B200_PLP_SMEM_TEXT"); if (s) e->smem_text = (uint32_t)atoi(s);
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
-    s = getenv("B200_PLP_GATHER_OCC"); e->gather_occ = s ? atoi(s) : 6;   // A/B: gather kernel built for 6 (80 registers) or 8 (64, small spills) CTAs per SM
     s = getenv("B200_PLP_GENERAL"); e->general = s ? atoi(s) : 0;   // 1: general mpileup path (thread-per-column size + write) for every configuration
     if (e->smem_text + 16 > 48 * 1024) {   // the attribute is per function and process-wide: only ever raise it (another handle may use more)
-        cudaFuncSetAttribute(k_mp_gather<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_mp_gather<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_mp_gather<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_mp_gather<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_mpileup_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_depth_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e->smem_text > 200 * 1024 - 16) e->smem_text = 200 * 1024 - 16;
@@ -798,7 +803,8 @@ static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
         k_ref_codes<<<nblk(e->ref_n, 256), 256, 0, e->stream>>>(e->ref, e->ref_n, e->ref_codes); e->launches++;
     }
     if (n > 0) {
-        k_prep1<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, acc); e->launches++;
+        const int gs = (int)std::min<int64_t>(nblk(n, 256), (int64_t)e->n_sm * 16);   // grid-stride: one set of accumulator atomics per block
+        k_prep1<<<gs, 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, acc); e->launches++;
         e->baq_ran = false;
         if (cf->mode == B200_MODE_MPILEUP && cf->baq && e->has_ref) {
             CK(cudaEventRecord(e->evB0, e->stream));
@@ -807,7 +813,7 @@ static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
             e->baq_ran = true;
         }
         k_prep2<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state); e->launches++;
-        k_build_desc<<<nblk(n, 256), 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, e->desc, e->endv, acc, e->win_base, e->cig_x, e->cig_y); e->launches++;
+        k_build_desc<<<gs, 256, 0, e->stream>>>(r, *cf, e->state, e->rlen, e->desc, e->endv, acc, e->win_base, e->cig_x, e->cig_y); e->launches++;
     }
     CK(cudaGetLastError());
     // ---- statistics back (also the sync point that validates the batch)
@@ -1079,8 +1085,8 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     CK(cudaEventRecord(e->evB, e->stream));
     {
         MpEntFmt gf; gf.v = fmt.v; gf.cf = fmt.cf; gf.E = e->ent; gf.E2 = e->ent2;
-        if (e->gather_occ == 8) k_mp_gather<8><<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
-        else k_mp_gather<6><<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        if (c->out_mapq) k_mp_gather<8, true><<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        else k_mp_gather<8, false><<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
         e->launches++;
     }
     CK(cudaEventRecord(e->ev1, e->stream));

@@ -67,43 +67,33 @@ __global__ void __launch_bounds__(256) k_mp_entries(View v, MpConf cf, int64_t n
                 const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(v.seq4 + (g >> 1)));
                 const int32_t c_of_g = d.rpos + (int32_t)(g - q0);          // column of query index g
                 uint32_t ent[8];
-                if (g >= lo && g + 8u <= hi) {
-                    // ---- interior group
-                    uint32_t failmask = ent_group8<HAS_REF>(v, refc, qq, s4, c_of_g, rev, minq, s_tab, ent);
-                    if (ends) {   // "^"+mapq at the read's first base, "$" at its last: at most one lane each
-                        const uint32_t kh = q0 - g, kt = qtail - g;
-                        if (kh < 8u && !((failmask >> kh) & 1u)) {
+                // all eight bases of the group are formatted (bytes beyond the read's ends belong to its neighbours in the
+                // arrays and are harmless to read); the ones inside [lo,hi) are kept
+                uint32_t failmask = ent_group8<HAS_REF>(v, refc, qq, s4, c_of_g, rev, minq, s_tab, ent);
+                const uint32_t kb = lo > g ? lo - g : 0u, ke = hi - g < 8u ? hi - g : 8u;
+                const uint32_t vmask = ((1u << ke) - 1u) & ~((1u << kb) - 1u);
+                failmask &= vmask;
+                if (ends) {   // "^"+mapq at the read's first base, "$" at its last: at most one lane each
+                    const uint32_t kh = q0 - g, kt = qtail - g;
+                    if (kh < 8u && ((vmask & ~failmask) >> kh) & 1u) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) if ((uint32_t)k == kh) ent[k] |= 0x80u;
-                            atomicAdd(&extra[c_of_g + (int32_t)kh], 2u);
-                        }
-                        if (kt < 8u && !((failmask >> kt) & 1u)) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) if ((uint32_t)k == kt) ent[k] |= 0x8000u;
-                            atomicAdd(&extra[c_of_g + (int32_t)kt], 1u);
-                        }
+                        for (int k = 0; k < 8; ++k) if ((uint32_t)k == kh) ent[k] |= 0x80u;
+                        atomicAdd(&extra[c_of_g + (int32_t)kh], 2u);
                     }
-                    while (failmask) { const int k = __ffs(failmask) - 1; failmask &= failmask - 1u; atomicAdd(&fail[c_of_g + k], 1u); }
+                    if (kt < 8u && ((vmask & ~failmask) >> kt) & 1u) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) if ((uint32_t)k == kt) ent[k] |= 0x8000u;
+                        atomicAdd(&extra[c_of_g + (int32_t)kt], 1u);
+                    }
+                }
+                while (failmask) { const int k = __ffs(failmask) - 1; failmask &= failmask - 1u; atomicAdd(&fail[c_of_g + k], 1u); }
+                if (vmask == 0xffu) {
                     uint4 w;
                     w.x = ent[0] | ent[1] << 16; w.y = ent[2] | ent[3] << 16; w.z = ent[4] | ent[5] << 16; w.w = ent[6] | ent[7] << 16;
                     *reinterpret_cast<uint4 *>(E + g) = w;
                 } else {
-                    // ---- group cut by the read's or the window's edge: base by base
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t qi = g + (uint32_t)k;
-                        if (qi < lo || qi >= hi) continue;
-                        const uint32_t q = ((k < 4 ? qq.x : qq.y) >> (8 * (k & 3))) & 0xffu;
-                        const uint32_t code = (s4 >> (8 * (k >> 1) + ((k & 1) ? 0 : 4))) & 0xfu;
-                        const int32_t c = c_of_g + k;
-                        const uint32_t rb = HAS_REF ? ref_nt16_at(v, refc, c) : 0x10u;
-                        uint32_t fl = 0;
-                        if (ends) fl = (qi == q0 ? 0x80u : 0u) | (qi == qtail ? 0x8000u : 0u);
-                        const uint32_t x = ent_plain(q, code, rb, rev, minq, fl, s_tab);
-                        E[qi] = (uint16_t)x;
-                        if (!x) atomicAdd(&fail[c], 1u);
-                        else if (fl) atomicAdd(&extra[c], ((fl & 0x80u) ? 2u : 0u) + ((fl & 0x8000u) ? 1u : 0u));
-                    }
+                    for (int k = 0; k < 8; ++k) if ((vmask >> k) & 1u) E[g + (uint32_t)k] = (uint16_t)ent[k];
                 }
             }
         } else {
@@ -135,6 +125,7 @@ struct MpEntFmt {
 // loads from global memory, and the entry loads of EIGHT reads are in flight before the first append (the entry of a read
 // that is not over the column, or not of the simple shape, is entry 0 of the array, discarded).
 // Same bytes as mp_line_write_ent (plp_core.h), which stays the reference implementation (emulation harness, deep tiles).
+template <bool OUT_MAPQ>
 __device__ __forceinline__ void gather_line_warp(const View &v, const MpConf &cf, int32_t c, bool active, const MpFileSz &s, char *p,
                                                  const uint16_t *E, const uint16_t *E2, uint4 *s_desc)
 {
@@ -145,23 +136,29 @@ __device__ __forceinline__ void gather_line_warp(const View &v, const MpConf &cf
     uint32_t so = on ? (uint32_t)(cur.ps - p) : 0u, qo = on ? (uint32_t)(cur.pq - p) : 0u, mo = on ? (uint32_t)(cur.pm - p) : 0u;
     const ReadRange rr = read_range(v, 0, c >> 5);            // the same for the 32 lanes
     const uint32_t kSimple = (uint32_t)RD_SIMPLE << 24;
-    const bool out_mapq = cf.out_mapq != 0;
+    // append entry e of read i.  The common entry (no flag, not special) is two byte stores and two cursor bumps, with no branch
+    // on e == 0: an empty entry stores a byte at the cursor without advancing it, the next real entry overwrites it -- and the two
+    // bytes just behind the sequence / quality strings (a tab each) are written AFTER the gather (see the end of this function)
     auto emit = [&](uint32_t pk, int32_t i, uint32_t e) {
-        if (!e) return;
-        const uint32_t mapq = (pk >> 16) & 0xffu;
-        if (e == ENT_SPECIAL) {
-            int q;
-            so += (uint32_t)ent_special(v, cf, i, c, p + so, q);
-            p[qo++] = (char)(q + 33 < 126 ? q + 33 : 126);
-        } else {
-            if (e & 0x8080u) {
+        if (e & 0x8080u) {                                   // "^" / "$" flags or the special marker: rare
+            const uint32_t mapq = (pk >> 16) & 0xffu;
+            if (e == ENT_SPECIAL) {
+                int q;
+                so += (uint32_t)ent_special(v, cf, i, c, p + so, q);
+                p[qo++] = (char)(q + 33 < 126 ? q + 33 : 126);
+            } else {
                 if (e & 0x80u) { p[so++] = '^'; p[so++] = (char)(mapq > 93u ? 126u : mapq + 33u); }
                 p[so++] = (char)(e & 0x7fu);
                 if (e & 0x8000u) p[so++] = '$';
-            } else p[so++] = (char)e;
-            p[qo++] = (char)((e >> 8) & 0x7fu);
+                p[qo++] = (char)((e >> 8) & 0x7fu);
+            }
+            if (OUT_MAPQ) p[mo++] = (char)umin32(mapq + 33u, 126u);
+        } else {
+            const uint32_t adv = e != 0u;
+            p[so] = (char)e; so += adv;
+            p[qo] = (char)(e >> 8); qo += adv;
+            if (OUT_MAPQ) { p[mo] = (char)umin32(((pk >> 16) & 0xffu) + 33u, 126u); mo += adv; }
         }
-        if (out_mapq) p[mo++] = (char)umin32(mapq + 33u, 126u);
     };
     auto one = [&](const uint4 &d, int32_t i) {      // general route for one read
         const uint32_t rel = (uint32_t)(c - (int32_t)d.x);
@@ -198,9 +195,14 @@ __device__ __forceinline__ void gather_line_warp(const View &v, const MpConf &cf
         }
         for (; r < cnt; ++r) one(s_desc[r], base + r);
     }
+    if (on) {   // the separators an empty trailing entry may have scribbled on
+        cur.pq[-1] = '\t';                                            // behind the sequence string
+        if (OUT_MAPQ) { cur.pm[-1] = '\t'; p[mo] = (cf.n_star_cols ? '\t' : '\n'); }
+        else p[qo] = (cf.n_star_cols ? '\t' : '\n');                   // behind the quality string: next column's tab or the newline
+    }
 }
 
-template <int MIN_CTAS>
+template <int MIN_CTAS, bool OUT_MAPQ>
 __global__ void __launch_bounds__(TILE, MIN_CTAS) k_mp_gather(MpEntFmt fmt, const uint32_t *len_in, const MpFileSz *st_in, const uint64_t *tile_base,
                                                               char *out, uint32_t smem_cap, int use_tma)
 {
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(TILE, MIN_CTAS) k_mp_gather(MpEntFmt fmt, cons
     const uint32_t phase = (uint32_t)(base & 15);
     if (total + phase <= smem_cap) {
         char *sb = s_text + phase;
-        gather_line_warp(fmt.v, fmt.cf, c < ncols ? c : ncols - 1, len != 0, stt, sb + off, fmt.E, fmt.E2, s_desc[threadIdx.x >> 5]);
+        gather_line_warp<OUT_MAPQ>(fmt.v, fmt.cf, c < ncols ? c : ncols - 1, len != 0, stt, sb + off, fmt.E, fmt.E2, s_desc[threadIdx.x >> 5]);
         __syncthreads();
         // ragged head (to the next 16 B boundary of the destination), aligned body, ragged tail
         char *g = out + base;

@@ -22,10 +22,16 @@ __global__ void k_link_next(const int64_t *prev, int64_t *next, int64_t n)
 }
 
 __global__ void k_overlap(RawSoA r, const int64_t *next, const uint8_t *state, const int32_t *rlen,
-                          const int64_t *file_start, int n_files)
+                          const int64_t *file_start, int n_files, int32_t *pairs, unsigned int *n_pairs)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < r.n) overlap_chain(r, i, next, state, rlen, file_start, n_files);
+    if (i < r.n) overlap_chain(r, i, next, state, rlen, file_start, n_files, pairs, n_pairs);
+}
+// the quality tweak of every collected pair, one thread per pair (the count stays on the device: no host round trip)
+__global__ void k_overlap_tweak(RawSoA r, const int32_t *pairs, const unsigned int *n_pairs)
+{
+    const unsigned int n = *n_pairs;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) tweak_overlap(r, pairs[2 * (size_t)k], pairs[2 * (size_t)k + 1]);
 }
 __global__ void k_depth_clip(RawSoA r, const int64_t *next, const uint8_t *state, const int32_t *rlen, int32_t *clip, int64_t win_base)
 {
@@ -48,7 +54,11 @@ static int link_chains(b200_engine *e, const RawSoA &r)
 int launch_overlap(b200_engine *e, const RawSoA &r)
 {
     if (link_chains(e, r)) return -1;
-    k_overlap<<<nblk(r.n, 128), 128, 0, e->stream>>>(r, e->next, e->state, e->rlen, e->file_start, e->n_files); e->launches++;
+    if (ensure(e, e->ov_pairs, e->cap_ov_pairs, (size_t)r.n + 2)) return -1;      // at most n/2 pairs of two indices
+    CK(cudaMemsetAsync(e->d_misc + 40, 0, 8, e->stream));
+    k_overlap<<<nblk(r.n, 128), 128, 0, e->stream>>>(r, e->next, e->state, e->rlen, e->file_start, e->n_files, e->ov_pairs, (unsigned int *)(e->d_misc + 40)); e->launches++;
+    const int gt = (int)std::min<int64_t>(nblk(r.n / 2 + 1, 128), (int64_t)e->n_sm * 16);
+    k_overlap_tweak<<<gt, 128, 0, e->stream>>>(r, e->ov_pairs, (const unsigned int *)(e->d_misc + 40)); e->launches++;
     CK(cudaGetLastError());
     return 0;
 }

@@ -318,9 +318,12 @@ PLP_HD void tweak_overlap(const RawSoA &r, int64_t ia, int64_t ib)
     }
 }
 
-// one thread per name chain: replay overlap_push / overlap_remove
+// one thread per name chain: replay overlap_push / overlap_remove.  pairs == nullptr: the quality tweak of a pair runs
+// right here (emulation harness); else the pair (first mate, second mate) is appended to pairs[] and tweaked by a second
+// kernel with one thread per PAIR -- a read takes part in at most one tweak, so the pairs are independent, and a warp
+// of tweaks keeps all its lanes busy where a warp of chains has ~15 % of them walking CIGARs.
 PLP_HD void overlap_chain(const RawSoA &r, int64_t i, const int64_t *next, const uint8_t *state, const int32_t *rlen,
-                          const int64_t *file_start, int n_files)
+                          const int64_t *file_start, int n_files, int32_t *pairs = nullptr, unsigned int *n_pairs = nullptr)
 {
     if (r.prev[i] >= 0 || next[i] < 0) return;   // not the head of a chain of >= 2
     int f = 0;
@@ -347,7 +350,12 @@ PLP_HD void overlap_chain(const RawSoA &r, int64_t i, const int64_t *next, const
         if (stored < 0) {
             if (r.mpos[x] >= pos || ((fl & 1) && r.mpos[x] == -1)) stored = x;
         } else {
-            tweak_overlap(r, stored, x);
+            if (pairs) {
+#if defined(__CUDA_ARCH__)
+                const unsigned int k = atomicAdd(n_pairs, 1u);
+                pairs[2 * (size_t)k] = (int32_t)stored; pairs[2 * (size_t)k + 1] = (int32_t)x;
+#endif
+            } else tweak_overlap(r, stored, x);
             stored = -1;
         }
     }
