@@ -24,6 +24,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 #include "plp_core.h"
 
 namespace baqr {
@@ -58,6 +59,33 @@ PLP_HD double emis_sel(uint64_t xw, int j, double em_match, double em_mis)
 }
 
 PLP_HD bool cell_valid(int i, int j, int l_ref) { const int k = i - BW + j; return k >= 1 && k <= l_ref; }
+
+// ---- per-row inputs, eight rows per load.  A row consumes one quality byte, one base nibble and one reference code; each is
+// a dependent, poorly cached access when fetched byte by byte (a warp's 32 reads touch 32 different sectors).  The streams
+// below hold the eight bytes that cover eight consecutive rows in one 64-bit register, with the next eight already in flight,
+// so a thread issues one load per stream per eight rows and has eight rows of FP64 work to hide it behind.
+// ld8: unaligned 8-byte little-endian load (device: two aligned 8-byte loads and a funnel shift -- up to 15 bytes past p are
+// touched, the staged arrays carry that slack; host harness: memcpy from padded buffers).
+PLP_HD uint64_t ld8(const uint8_t *p)
+{
+#if defined(__CUDA_ARCH__)
+    const unsigned long long a = (unsigned long long)p;
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~7ull);
+    const uint32_t sh = (uint32_t)(a & 7ull) * 8u;
+    const uint64_t lo = w[0], hi = w[1];
+    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+#else
+    uint64_t v; memcpy(&v, p, 8); return v;
+#endif
+}
+PLP_HD uint32_t byte_of(uint64_t w, int k) { return (uint32_t)(w >> (8 * k)) & 0xffu; }
+// query base qi of a read whose first base is nibble qoff of seq4, from the 8-byte word loaded at byte (qoff + (qi & ~7)) >> 1
+PLP_HD int nib_at(uint64_t w, uint32_t qoff, int base, int qi)     // word loaded at byte (qoff + base) >> 1, base <= qi < base + 8
+{
+    const uint32_t g = qoff + (uint32_t)qi, g0 = qoff + (uint32_t)base;
+    return (int)((w >> (8u * ((g >> 1) - (g0 >> 1)) + ((~g & 1u) << 2))) & 0xfu);
+}
+PLP_HD int nib_of(uint64_t w, uint32_t qoff, int qi) { return nib_at(w, qoff, qi & ~7, qi); }
 
 // forward row i >= 2 from row i-1 (scaled) held in M/I/D; returns the row sum s[i] (cells left UNSCALED)
 template <bool EDGE>
@@ -110,14 +138,23 @@ PLP_HD int phred_of(double xx, const double *qthr)
 
 // One read.  Mem provides
 //   int  ref_code(int p)                         code 0..4 of window position p (0-based, p < l_ref)
+//   uint64_t ref8(int p)                         codes of window positions p..p+7 (p >= 0, multiple of 8), one per byte; 4 beyond the sequence
 //   void put_row(int i, M, I, double inv)        scaled forward M/I states of row i and 1/s[i]
 //   void fence()                                 rows written so far are visible to the fetches that follow
 //   void fetch(int i)                            start bringing row i back (asynchronous on the device)
 //   void wait(int pending)                       all but the `pending` most recent fetches have landed
 //   void get(int i, int j, double &fM, double &fI);   double inv(int i)
 //   void put_word(int j, int32_t w);  int32_t get_word(int j)        per-base scratch
+// Checkpoint mode (K > 0): the forward pass keeps only every K-th row (rows 1, K+1, 2K+1, ... with their D states and the
+// reference window), and the backward pass re-runs the forward recurrence over one K-row segment at a time into a K-row
+// buffer that is rewritten segment after segment -- small enough to live in L2 -- before it walks the segment backwards.
+// The recomputation starts from bit-identical inputs and evaluates the same expressions, so every stored value is the
+// one the single forward pass produced.  Costs the forward arithmetic twice (22 of 53 operations per cell), saves the
+// (l_query x 248 B) round trip through HBM.  put_row / fetch / get / inv then address row (i-1) % K of the buffer, and
+//   void put_ckpt(int s, M, I, D, double inv, uint64_t win);  void get_ckpt(int s, M, I, D, double &inv, uint64_t &win)
+//   void park(M, I);  void unpark(M, I)          backward state of the previous segment, out of the registers during a recomputation
 // q2pf[q] = (double)(float)pow(10, -q/10.)   qthr = break points (see baq.cuh)
-template <class Mem>
+template <int K, class Mem>
 PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff, int lq, int l_ref, int64_t pos, int64_t xb,
                      const uint32_t *cg, int n_cigar, const double *q2pf, const double *qthr, bool extend = true)
 {
@@ -143,18 +180,22 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         }
 #pragma unroll
         for (int j = BW; j < NB; ++j) if (cell_valid(1, j, l_ref)) { M[j] /= sum; I[j] /= sum; }
-        mem.put_row(1, M, I, 1. / sum);
+        if (K == 0) mem.put_row(1, M, I, 1. / sum); else mem.put_ckpt(0, M, I, D, 1. / sum, win);
         s_lq = sum;
     }
-    // the inputs of a row (one quality byte, one base byte, one reference code) are fetched ONE ROW AHEAD: each is a
-    // dependent, poorly cached byte load, and a row is ~1000 cycles of FP64 work to hide it behind
-    uint32_t nq = lq > 1 ? qual[1] : 0, ns = lq > 1 ? seq4[(qoff + 1u) >> 1] : 0;
-    int nr = (BW + 1 < l_ref) ? mem.ref_code(BW + 1) : 4;
+    // the inputs of a row (query base i-1, window position i + 6 entering at cell 14) come from the 8-row streams (see ld8)
+    const uint8_t *sq = seq4 + (qoff >> 1);                 // byte of base 0 (its high or low nibble: qoff & 1)
+    const uint32_t qpar = qoff & 1u;
+    uint64_t qw = ld8(qual), sw = ld8(sq), rw = 0;
+    uint64_t qn = lq > 8 ? ld8(qual + 8) : 0, sn = lq > 8 ? ld8(sq + ((qpar + 8u) >> 1)) : 0, rn = mem.ref8(BW + 1);   // row 2 opens block 8 of the reference stream
     for (int i = 2; i <= lq; ++i) {
-        const uint32_t cq = nq, cs = ns; const int cr = nr;          // row i: query base i-1, window position i + 6 enters
-        if (i < lq) { nq = qual[i]; ns = seq4[(qoff + (uint32_t)i) >> 1]; nr = (i + BW < l_ref) ? mem.ref_code(i + BW) : 4; }
+        const int qi = i - 1, rp = i + BW - 1;
+        if ((qi & 7) == 0) { qw = qn; sw = sn; if (qi + 8 < lq) { qn = ld8(qual + qi + 8); sn = ld8(sq + ((qpar + (uint32_t)qi + 8u) >> 1)); } }
+        if ((rp & 7) == 0) { rw = rn; rn = mem.ref8(rp + 8); }
+        const uint32_t cq = byte_of(qw, qi & 7);
+        const int cr = rp < l_ref ? (int)byte_of(rw, rp & 7) : 4;
         win = (win >> 4) | ((uint64_t)cr << (4 * (NB - 1)));
-        const int qc = plp::nt16_int_of((int)((cs >> ((~(qoff + (uint32_t)(i - 1)) & 1u) << 2)) & 0xfu));
+        const int qc = plp::nt16_int_of(nib_of(sw, qpar, qi));
         const double ql = q2pf[cq];
         const double em_match = qc > 3 ? 1. : 1. - ql, em_mis = qc > 3 ? 1. : ql * BAQR_EM;
         const uint64_t xw = win ^ (kRep * (uint64_t)(qc & 7));
@@ -170,11 +211,11 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
 #pragma unroll
             for (int j = 0; j < NB; ++j) if (cell_valid(i, j, l_ref)) { M[j] *= inv; I[j] *= inv; D[j] *= inv; }
         }
-        mem.put_row(i, M, I, inv);
+        if (K == 0) mem.put_row(i, M, I, inv);
+        else if ((i - 1) % (K ? K : 1) == 0) mem.put_ckpt((i - 1) / (K ? K : 1), M, I, D, inv, win);
         s_lq = sum;
     }
-    mem.fence();
-    mem.fetch(lq);
+    if (K == 0) mem.fence();
     double s_last = 0.;      // ---- termination
 #pragma unroll
     for (int j = 0; j < NB; ++j) if (cell_valid(lq, j, l_ref)) s_last += M[j] * p.sM + I[j] * p.sM;
@@ -184,37 +225,88 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         for (int j = 0; j < NB; ++j) { const double v = cell_valid(lq, j, l_ref) ? bv : 0.; M[j] = v; I[j] = v; }
     }
     // `win` holds positions lq + j - 8: exactly what backward row lq-1 compares against (position k = i - 7 + j)
-    // backward row i uses query base i and, from row lq-2 down, window position i - 7 entering at cell 0: one row ahead again
-    nq = lq > 1 ? qual[lq - 1] : 0; ns = lq > 1 ? seq4[(qoff + (uint32_t)(lq - 1)) >> 1] : 0; nr = 4;
-    for (int i = lq; i >= 1; --i) {
-        if (i > 1) mem.fetch(i - 1);
+    // backward row i uses query base i and, from row lq-2 down, window position i - 7 entering at cell 0: the same 8-row
+    // streams, walked downwards (block of index x = x & ~7; the block below is in flight while a block is consumed)
+    const int r0 = lq - 2 - BW;                              // first position to enter (row lq-2)
+    {
+        const int q0 = (lq - 1) & ~7, rb = r0 >= 0 ? (r0 & ~7) : 0;
+        qw = ld8(qual + q0); sw = ld8(sq + ((qpar + (uint32_t)q0) >> 1));
+        if (q0 >= 8) { qn = ld8(qual + q0 - 8); sn = ld8(sq + ((qpar + (uint32_t)q0 - 8u) >> 1)); }
+        rw = mem.ref8(rb); if (rb >= 8) rn = mem.ref8(rb - 8);
+    }
+    // the rows are walked in segments [i0, i1]: one segment (all rows) when every forward row was kept, K-row segments
+    // re-derived from their checkpoint otherwise
+    const int nseg = K ? (lq + (K ? K : 1) - 1) / (K ? K : 1) : 1;
+    for (int sgm = nseg - 1; sgm >= 0; --sgm) {
+    const int i0 = K ? sgm * K + 1 : 1, i1 = K ? (i0 + K - 1 < lq ? i0 + K - 1 : lq) : lq;
+    if (K) {
+        // ---- forward rows i0 .. i1 again, from the checkpoint of row i0, into the segment buffer
+        const bool parked = true;      // the backward state (for the last segment: its initial values) leaves the registers while the forward rows are re-derived
+        const uint64_t qv = ld8(qual + i0), sv = ld8(sq + ((qpar + (uint32_t)i0) >> 1));     // query bases i0 .. i0+7 (rows i0+1 ..)
+        if (parked) mem.park(M, I);
+        {
+            double fM[NB], fI[NB], fD[NB]; double finv; uint64_t fwin;
+            mem.get_ckpt(sgm, fM, fI, fD, finv, fwin);
+            mem.put_row(i0, fM, fI, finv);
+#pragma unroll 1
+            for (int i = i0 + 1; i <= i1; ++i) {                 // one copy of the row code (the kernel is instruction-cache bound otherwise)
+                {
+                    const int qi = i - 1, rp = i + BW - 1;
+                    const int crr = rp < l_ref ? mem.ref_code(rp) : 4;
+                    fwin = (fwin >> 4) | ((uint64_t)crr << (4 * (NB - 1)));
+                    const int qc = plp::nt16_int_of(nib_at(sv, qpar, i0, qi));
+                    const double ql = q2pf[byte_of(qv, qi - i0)];
+                    const double em_match = qc > 3 ? 1. : 1. - ql, em_mis = qc > 3 ? 1. : ql * BAQR_EM;
+                    const uint64_t xw = fwin ^ (kRep * (uint64_t)(qc & 7));
+                    double sum;
+                    if (i > BW && i + BW <= l_ref) {
+                        sum = fwd_row<false>(fM, fI, fD, p, xw, em_match, em_mis, i, l_ref);
+                        finv = 1. / sum;
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) { fM[j] *= finv; fI[j] *= finv; fD[j] *= finv; }
+                    } else {
+                        sum = fwd_row<true>(fM, fI, fD, p, xw, em_match, em_mis, i, l_ref);
+                        finv = 1. / sum;
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) if (cell_valid(i, j, l_ref)) { fM[j] *= finv; fI[j] *= finv; fD[j] *= finv; }
+                    }
+                    mem.put_row(i, fM, fI, finv);
+                }
+            }
+        }
+        mem.fence();
+        if (parked) mem.unpark(M, I);
+    }
+    mem.fetch(i1);
+    for (int i = i1; i >= i0; --i) {
+        if (i > i0) mem.fetch(i - 1);
         if (i < lq) {
-            const uint32_t cq = nq, cs = ns; const int cr = nr;
-            if (i > 1) { nq = qual[i - 1]; ns = seq4[(qoff + (uint32_t)(i - 1)) >> 1]; const int pn = i - 1 - BW; nr = (pn >= 0 && pn < l_ref) ? mem.ref_code(pn) : 4; }
+            const int qi = i, rp = i - BW;
+            if ((qi & 7) == 7 && qi != lq - 1) { qw = qn; sw = sn; if (qi >= 15) { qn = ld8(qual + qi - 15); sn = ld8(sq + ((qpar + (uint32_t)qi - 15u) >> 1)); } }
+            if (rp < r0 && rp >= 0 && (rp & 7) == 7) { rw = rn; if (rp >= 15) rn = mem.ref8(rp - 15); }
+            const uint32_t cq = byte_of(qw, qi & 7);
+            const int cr = (rp >= 0 && rp < l_ref) ? (int)byte_of(rw, rp & 7) : 4;
             if (i < lq - 1) win = ((win << 4) & kMask) | (uint64_t)cr;
-            const int qc = plp::nt16_int_of((int)((cs >> ((~(qoff + (uint32_t)i) & 1u) << 2)) & 0xfu));
+            const int qc = plp::nt16_int_of(nib_of(sw, qpar, qi));
             const double ql = q2pf[cq];
             const double em_match = qc > 3 ? 1. : 1. - ql, em_mis = qc > 3 ? 1. : ql * BAQR_EM;
             const uint64_t xw = win ^ (kRep * (uint64_t)(qc & 7));
             if (i > BW && i + BW < l_ref) {
                 bwd_row<false>(M, I, p, xw, em_match, em_mis, i, l_ref);
-                mem.wait(1);                                         // row i (fetched one iteration ago) has landed
+                mem.wait(i > i0 ? 1 : 0);                            // row i (fetched one iteration ago) has landed
                 const double ys = mem.inv(i);
 #pragma unroll
                 for (int j = 0; j < NB; ++j) { M[j] *= ys; I[j] *= ys; }
             } else {
                 bwd_row<true>(M, I, p, xw, em_match, em_mis, i, l_ref);
-                mem.wait(i > 1 ? 1 : 0);
+                mem.wait(i > i0 ? 1 : 0);
                 const double ys = mem.inv(i);
 #pragma unroll
                 for (int j = 0; j < NB; ++j) if (cell_valid(i, j, l_ref)) { M[j] *= ys; I[j] *= ys; }
             }
         } else {
-            // row lq: nothing to compute; prime the inputs of row lq-1 (query base lq-1 is already in nq/ns) -- its reference
-            // window is `win` as it stands, the first position to ENTER is (lq-2) - 7 for row lq-2
-            const int pn = lq - 2 - BW;
-            nr = (pn >= 0 && pn < l_ref) ? mem.ref_code(pn) : 4;
-            mem.wait(i > 1 ? 1 : 0);
+            // row lq: nothing to compute (the streams are primed above)
+            mem.wait(i > i0 ? 1 : 0);
         }
         // ---- MAP of row i (cells outside the band are zero on both sides: they add 0 and never exceed the maximum)
         double sum = 0., mx = 0.; int best = -1;
@@ -230,6 +322,7 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         const int kq = phred_of(1. - mx, qthr);
         mem.put_word(i - 1, (int32_t)((uint32_t)max_k << 8 | (uint32_t)kq));
     }
+    }   // segments
     // ---- sam_prob_realn epilogue (APPLY): per match run, zero the bases whose MAP state is not the aligned match,
     // with EXTEND replace each by the smaller of the running maxima from both ends of the run, cap the quality
     int64_t x = pos; int y = 0;
@@ -238,22 +331,36 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         if (plp::is_mop(op)) {
             if (l > lq - y) l = lq - y;
             if (l > 0) {
+                // eight bases per step: the scratch words (and, on the way back, the quality bytes) of a step are independent loads,
+                // issued together -- a base-by-base loop exposes one full memory round trip per base
                 int left = 0;
-                for (int j = y; j < y + l; ++j) {
-                    const int32_t w = mem.get_word(j);
-                    const int st = w >> 8, kq = w & 0xff;
-                    const int t = ((st & 3) != 0 || (int64_t)(st >> 2) != x - xb + (j - y)) ? 0 : kq;
-                    left = (extend && left > t) ? left : t;
-                    mem.put_word(j, t | left << 8);
+                for (int j0 = y; j0 < y + l; j0 += 8) {
+                    const int n = y + l - j0 < 8 ? y + l - j0 : 8;
+                    int32_t w[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) w[u] = u < n ? mem.get_word(j0 + u) : 0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (u < n) {
+                        const int j = j0 + u;
+                        const int st = w[u] >> 8, kq = w[u] & 0xff;
+                        const int t = ((st & 3) != 0 || (int64_t)(st >> 2) != x - xb + (j - y)) ? 0 : kq;
+                        left = (extend && left > t) ? left : t;
+                        mem.put_word(j, t | left << 8);
+                    }
                 }
                 int rght = 0;
-                for (int j = y + l - 1; j >= y; --j) {
-                    const int32_t w = mem.get_word(j);
-                    const int t = w & 0xff, lf = w >> 8;
-                    rght = (extend && rght > t) ? rght : t;
-                    const int bq = lf < rght ? lf : rght;
-                    const int qv = qual[j];
-                    qual[j] = (uint8_t)(qv - (qv <= bq ? 0 : qv - bq));
+                for (int j1 = y + l - 1; j1 >= y; j1 -= 8) {
+                    const int n = j1 - y + 1 < 8 ? j1 - y + 1 : 8;
+                    int32_t w[8]; int qv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { w[u] = u < n ? mem.get_word(j1 - u) : 0; qv[u] = u < n ? qual[j1 - u] : 0; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (u < n) {
+                        const int t = w[u] & 0xff, lf = w[u] >> 8;
+                        rght = (extend && rght > t) ? rght : t;
+                        const int bq = lf < rght ? lf : rght;
+                        qual[j1 - u] = (uint8_t)(qv[u] - (qv[u] <= bq ? 0 : qv[u] - bq));
+                    }
                 }
             }
             x += l; y += l;

@@ -617,8 +617,8 @@ extern "C" int b200_engine_create(int device, b200_engine_t **out)
     s = getenv("B200_PLP_TMA"); e->use_tma = s ? atoi(s) : 1;
     s = getenv("B200_PLP_GENERAL"); e->general = s ? atoi(s) : 0;   // 1: general mpileup path (thread-per-column size + write) for every configuration
     if (e->smem_text + 16 > 48 * 1024) {   // the attribute is per function and process-wide: only ever raise it (another handle may use more)
-        cudaFuncSetAttribute(k_mp_gather<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(k_mp_gather<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_mp_gather<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_mp_gather<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_mpileup_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(k_depth_write, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e->smem_text > 200 * 1024 - 16) e->smem_text = 200 * 1024 - 16;
@@ -635,7 +635,7 @@ extern "C" void b200_engine_destroy(b200_engine_t *e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     e->free_all();
-    cudaFree(e->d_acc); cudaFree(e->d_misc);
+    cudaFree(e->d_acc); cudaFree(e->d_misc); if (e->d_gfmt) cudaFree(e->d_gfmt);
     cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->evA); cudaEventDestroy(e->evB);
     cudaEventDestroy(e->evB0); cudaEventDestroy(e->evB1);
     cudaStreamDestroy(e->stream);
@@ -650,6 +650,52 @@ template <class T> static int h2d(b200_engine *e, T *&dp, size_t &cap, const T *
 }
 #define H2D(field, hp, n) do { if (h2d(e, e->field, e->cap_##field, (hp), (size_t)(n))) return -1; } while (0)
 
+
+// Exact test for "the max-depth rule cannot fire": bam_plp_push drops a read only when more than maxcnt accepted reads of its
+// file are still buffered at its start, i.e. their closed intervals [start, end] hold one position.  The largest such count is
+// the maximum of the prefix sum of a +1 / -1 difference array over the kept reads (positions outside the staged columns are
+// folded onto the first / last one: an over-estimate, which is the safe side).
+__global__ void k_cov_diff(const uint8_t *state, const ReadDesc *desc, const int32_t *rlen, int64_t i0, int64_t i1, int32_t ncols, int32_t *diff)
+{
+    const int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1 || state[i] != ST_KEEP) return;
+    const int64_t p = desc[i].rpos, q = p + (int64_t)rlen[i] + 1;
+    const int32_t a = (int32_t)(p < 0 ? 0 : (p > ncols ? ncols : p)), b = (int32_t)(q < 1 ? 1 : (q > (int64_t)ncols + 1 ? (int64_t)ncols + 1 : q));
+    atomicAdd(&diff[a], 1); atomicAdd(&diff[b], -1);
+}
+__global__ void k_max_i32(const int32_t *x, int32_t n, int *out)
+{
+    int m = INT32_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, x[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+// largest number of kept reads of one file whose closed intervals share a position (see k_cov_diff)
+static int max_buffered_reads(b200_engine *e, int *out)
+{
+    const int32_t ncols = e->ncols_max + 1;
+    ENSURE(ss_diff, (size_t)ncols + 3); ENSURE(ss_nplp, (size_t)ncols + 3);
+    const int nbs = nblk((int64_t)ncols + 2, 1024);
+    ENSURE(status2, (size_t)nbs + 1);
+    int best = 0;
+    for (int f = 0; f < e->n_files; ++f) {
+        const int64_t i0 = e->h_file_start[f], i1 = e->h_file_start[f + 1];
+        if (i1 <= i0) continue;
+        CK(cudaMemsetAsync(e->ss_diff, 0, ((size_t)ncols + 2) * 4, e->stream));
+        CK(cudaMemsetAsync(e->status2, 0, ((size_t)nbs + 1) * 8, e->stream));
+        CK(cudaMemsetAsync(e->d_misc + 2, 0, 16, e->stream));
+        k_cov_diff<<<nblk(i1 - i0, 256), 256, 0, e->stream>>>(e->state, e->desc, e->rlen, i0, i1, ncols, e->ss_diff); e->launches++;
+        k_ss_scan<<<nbs, 256, 0, e->stream>>>(e->ss_diff, e->ss_nplp, ncols + 2, e->status2, (uint32_t *)(e->d_misc + 2)); e->launches++;
+        k_max_i32<<<e->n_sm * 4, 256, 0, e->stream>>>(e->ss_nplp, ncols + 2, (int *)(e->d_misc + 3)); e->launches++;
+        int m = 0;
+        CK(cudaMemcpyAsync(&m, e->d_misc + 3, 4, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (m > best) best = m;
+    }
+    *out = best;
+    return 0;
+}
 
 // max-depth rule of bam_plp_push, evaluated on the host only when a column could
 // hold more than maxcnt reads (sequential by nature).
@@ -842,7 +888,13 @@ static int stage_device(b200_engine *e, b200_stage_stats_t *stats)
     if (n > 0) {
         if (build_ranges(e, &max_range)) return -1;
         // max-depth rule (bam_plp_push): only reachable when some column can hold > maxcnt reads
-        if (cf->mode != B200_MODE_DEPTH && cf->max_depth > 0 && 2LL * max_range + 1 > (int64_t)cf->max_depth) {
+        bool may_fire = cf->mode != B200_MODE_DEPTH && cf->max_depth > 0 && 2LL * max_range + 1 > (int64_t)cf->max_depth;
+        if (may_fire) {   // the slice bound is loose (deep amplicons): exact count on the device before falling back to the host sweep
+            int mb = 0;
+            if (max_buffered_reads(e, &mb)) return -1;
+            may_fire = (int64_t)mb + 1 > (int64_t)cf->max_depth;
+        }
+        if (may_fire) {
             e->h_rlen_tmp.resize((size_t)n);
             CK(cudaMemcpyAsync(e->h_rlen_tmp.data(), e->rlen, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
             if (apply_maxcnt_host(e, n, cf->max_depth)) return -1;
@@ -1057,7 +1109,7 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     ENSURE(col_n, (size_t)nt * TILE + 1);
     ENSURE(col_state, ((size_t)nt * TILE * sizeof(MpFileSz) + 7) / 8 + 1);
     ENSURE(tile_total, (size_t)nt + 1); ENSURE(col_off, (size_t)nt + 2);
-    ENSURE(ent, e->qual_bytes + 16); ENSURE(ent2, (size_t)e->sum_rlen_gen + 16);
+    ENSURE(ent, e->qual_bytes + 64 + ENT_PAD); ENSURE(ent2, (size_t)e->sum_rlen_gen + 64 + ENT_PAD);   // front pad + slack for the gather's 80-byte fetches
     const int nb = nblk(nt, 256);
     ENSURE(status, (size_t)nb + 1);
     CK(cudaMemsetAsync(e->status, 0, ((size_t)nb + 1) * 8, e->stream));
@@ -1074,8 +1126,8 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     {
         const int64_t want_blocks = (e->n * 32 + 255) / 256;
         const int rb = (int)std::max<int64_t>(1, std::min<int64_t>(want_blocks, (int64_t)e->n_sm * 16));
-        if (e->has_ref) k_mp_entries<true><<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, e->ref_codes, e->ss_diff, e->ss_fail, e->ss_extra, e->ent, e->ent2, e->d_misc + 3, e->desc);
-        else k_mp_entries<false><<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, nullptr, e->ss_diff, e->ss_fail, e->ss_extra, e->ent, e->ent2, e->d_misc + 3, e->desc);
+        if (e->has_ref) k_mp_entries<true><<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, e->ref_codes, e->ss_diff, e->ss_fail, e->ss_extra, e->ent + ENT_PAD, e->ent2 + ENT_PAD, e->d_misc + 3, e->desc);
+        else k_mp_entries<false><<<rb, 256, 0, e->stream>>>(fmt.v, fmt.cf, e->n, nullptr, e->ss_diff, e->ss_fail, e->ss_extra, e->ent + ENT_PAD, e->ent2 + ENT_PAD, e->d_misc + 3, e->desc);
         e->launches++;
         k_ss_scan<<<nbs, 256, 0, e->stream>>>(e->ss_diff, e->ss_nplp, ncols + 1, e->status2, (uint32_t *)(e->d_misc + 2)); e->launches++;
         k_ss_cols<<<nt, TILE, 0, e->stream>>>(fmt.v, fmt.cf, e->ss_nplp, e->ss_fail, e->ss_extra, e->col_n, (MpFileSz *)e->col_state, e->tile_total); e->launches++;
@@ -1084,9 +1136,22 @@ extern "C" int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c,
     k_scan_u32_to_u64<<<nb, 256, 0, e->stream>>>(e->tile_total, e->col_off, nt, e->status, (uint32_t *)e->d_misc); e->launches++;
     CK(cudaEventRecord(e->evB, e->stream));
     {
-        MpEntFmt gf; gf.v = fmt.v; gf.cf = fmt.cf; gf.E = e->ent; gf.E2 = e->ent2;
-        if (c->out_mapq) k_mp_gather<8, true><<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
-        else k_mp_gather<8, false><<<nt, TILE, e->smem_text + 16, e->stream>>>(gf, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, e->smem_text, e->use_tma);
+        MpEntFmt gf; gf.v = fmt.v; gf.cf = fmt.cf; gf.E = e->ent + ENT_PAD; gf.E2 = e->ent2 + ENT_PAD;
+        // the cold paths of the gather read the same structure from global memory (see mpileup_ent.cuh)
+        if (!e->d_gfmt) CK(cudaMalloc(&e->d_gfmt, sizeof(MpEntFmt)));
+        CK(cudaMemcpyAsync(e->d_gfmt, &gf, sizeof gf, cudaMemcpyHostToDevice, e->stream));
+        const MpEntFmt *dg = (const MpEntFmt *)e->d_gfmt;
+        // shared-memory budget of a tile's text: 9/8 of the average tile's upper bound (itself ~1.4x the text; deeper tiles format
+        // straight into HBM), at most the configured cap -- a smaller footprint keeps more CTAs resident (30x/150 bp: 16 KB -> 7
+        // per SM instead of 5)
+        uint32_t cap = e->smem_text;
+        {
+            const uint64_t avg_tile = bound / (uint64_t)nt;
+            const uint64_t want = std::max<uint64_t>(12 * 1024, (avg_tile * 9 / 8 + 1023) & ~1023ull);
+            if (want < cap) cap = (uint32_t)want;
+        }
+        if (c->out_mapq) k_mp_gather<7, true><<<nt, TILE, cap + 16, e->stream>>>(gf, dg, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, cap, e->use_tma);
+        else k_mp_gather<7, false><<<nt, TILE, cap + 16, e->stream>>>(gf, dg, e->col_n, (const MpFileSz *)e->col_state, e->col_off, e->out, cap, e->use_tma);
         e->launches++;
     }
     CK(cudaEventRecord(e->ev1, e->stream));

@@ -729,6 +729,69 @@ PLP_HD uint32_t ent_plain(uint32_t q, uint32_t code, uint32_t rb, uint32_t rev, 
     return (uint32_t)tab[rev * 16u + code] | umin32(q + 33u, 126u) << 8 | flags;
 }
 
+// ---- eight entries at once, SIMD within 32-bit words (the read-major entry pass of mpileup_ent.cuh).
+// byte permute: result byte i = byte (sel nibble i) of the 8 bytes {b:7..4, a:3..0}  (PRMT on the device)
+PLP_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t w = (uint64_t)b << 32 | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((w >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
+// the 16 sequence characters of one strand as four words of a register table: t[k] holds codes 4k .. 4k+3
+struct EntTab { uint32_t t0, t1, t2, t3; };
+PLP_HD EntTab ent_tab(uint32_t rev)
+{
+    EntTab t;   // ".ACM" "GRSV" "TWYH" "KDBN" little-endian; the reverse strand is the lower-case row with ','
+    t.t0 = 0x4d43412eu; t.t1 = 0x56535247u; t.t2 = 0x48595754u; t.t3 = 0x4e42444bu;
+    if (rev) { t.t0 = 0x6d63612cu; t.t1 |= 0x20202020u; t.t2 |= 0x20202020u; t.t3 |= 0x20202020u; }
+    return t;
+}
+// quality characters of four quality bytes: min(q + 33, 126) per byte
+PLP_HD uint32_t ent_qchar4(uint32_t q)
+{
+    const uint32_t t = (q & 0x7f7f7f7fu) + 0x21212121u;                       // q7 + 33 <= 160: no carry between bytes
+    const uint32_t m = ((((t + 0x01010101u) | q) & 0x80808080u) >> 7) * 0xffu;  // bytes with q7 + 33 >= 127 or q >= 128
+    return (t & ~m) | (0x7e7e7e7eu & m);
+}
+// 0xff in every byte whose quality is below minq (0 <= minq <= 127; bytes >= 128 never fail)
+PLP_HD uint32_t ent_fail4(uint32_t q, uint32_t minq4)
+{
+    const uint32_t ge = ((((q & 0x7f7f7f7fu) | 0x80808080u) - minq4) | q) & 0x80808080u;   // bit 7: q >= minq
+    return ((ge ^ 0x80808080u) >> 7) * 0xffu;
+}
+// sequence characters of the four codes in nibbles 0..3 of h (natural order), through the register table
+PLP_HD uint32_t ent_schar4(uint32_t h, const EntTab &t)
+{
+    const uint32_t sel = h & 0x7777u;
+    const uint32_t lo = bperm(t.t0, t.t1, sel), hi = bperm(t.t2, t.t3, sel);
+    return bperm(lo, hi, ((h & 0x8888u) >> 1) | 0x3210u);
+}
+// Eight consecutive bases: qx/qy their quality bytes, s4 their four sequence bytes (even base in the high nibble, BAM order),
+// r8 the reference codes of their columns as eight nibbles in natural order (has_ref; a base equal to it prints '.' / ','),
+// minq4 = minq in every byte (0..127).  Entries leave as four words (entry k in half k&1 of word k>>1), WITHOUT the
+// "^" / "$" flags; returns bit k set when base k fails -Q.
+PLP_HD uint32_t ent_group8_swar(uint32_t qx, uint32_t qy, uint32_t s4, bool has_ref, uint32_t r8, const EntTab &t, uint32_t minq4, uint32_t (&w)[4])
+{
+    uint32_t n = ((s4 & 0x0f0f0f0fu) << 4) | ((s4 >> 4) & 0x0f0f0f0fu);         // nibble k = code of base k
+    if (has_ref) {
+        const uint32_t z = n ^ r8;
+        const uint32_t ne = (((z & 0x77777777u) + 0x77777777u) | z) & 0x88888888u;   // bit 3 of a nibble: codes differ
+        n &= ~(((ne ^ 0x88888888u) >> 3) * 0xfu);
+    }
+    const uint32_t fx = ent_fail4(qx, minq4), fy = ent_fail4(qy, minq4);
+    const uint32_t cx = ent_schar4(n, t) & ~fx, cy = ent_schar4(n >> 16, t) & ~fy;
+    const uint32_t ax = ent_qchar4(qx) & ~fx, ay = ent_qchar4(qy) & ~fy;
+    w[0] = bperm(cx, ax, 0x5140u); w[1] = bperm(cx, ax, 0x7362u);
+    w[2] = bperm(cy, ay, 0x5140u); w[3] = bperm(cy, ay, 0x7362u);
+    // one bit per failing base: bits 0,8,16,24 of (f >> 7) gathered by a multiply (partial products never collide)
+    return ((((fx & 0x01010101u) * 0x00204081u) >> 21) & 0xfu) | ((((fy & 0x01010101u) * 0x00204081u) >> 17) & 0xf0u);
+}
+
 // entry of read d (any shape) at column c through the generic cursor; extra = bytes the entry prints beyond its
 // one sequence character ("^"+mapq, "$", indel text): what the size pass adds to the column
 PLP_HD uint32_t ent_generic(const View &v, const MpConf &cf, const ReadDesc &d, int32_t c, uint32_t rb, const uint8_t *tab, uint32_t &extra)

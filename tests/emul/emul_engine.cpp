@@ -253,6 +253,33 @@ int b200_mpileup_text(b200_engine_t *e, const b200_mpileup_conf_t *c, char *out,
                     if (!x) fail[(size_t)c]++;
                     else if (fl) extra[(size_t)c] += ((fl & 0x80u) ? 2u : 0u) + ((fl & 0x8000u) ? 1u : 0u);
                 }
+                // cross-check of the SIMD-in-word formatter the device entry pass uses (ent_group8_swar) against the per-base ent_plain
+                if (cf.min_baseQ <= 127) {
+                    const uint32_t lo = q0 + (uint32_t)(a - d.rpos), hi = q0 + (uint32_t)(b - d.rpos);
+                    const EntTab etab = ent_tab(rev);
+                    const uint32_t minq4 = (uint32_t)(cf.min_baseQ > 0 ? cf.min_baseQ : 0) * 0x01010101u;
+                    for (uint32_t g = lo & ~7u; g < hi; g += 8) {
+                        uint32_t qx = 0, qy = 0, s4 = 0, r8 = 0;
+                        for (uint32_t k = 0; k < 8; ++k) {
+                            const size_t qi = (size_t)g + k;
+                            const uint32_t q = qi < e->qual.size() ? e->qual[qi] : 0;
+                            if (k < 4) qx |= q << (8 * k); else qy |= q << (8 * (k - 4));
+                            const int32_t cc = d.rpos + (int32_t)(g + k - q0);
+                            r8 |= (ent_ref_code(v, cc) & 0xfu) << (4 * k);
+                        }
+                        for (uint32_t k = 0; k < 4; ++k) { const size_t bi = (size_t)(g >> 1) + k; s4 |= (uint32_t)(bi < e->seq4.size() ? e->seq4[bi] : 0) << (8 * k); }
+                        uint32_t w[4];
+                        const uint32_t fm = ent_group8_swar(qx, qy, s4, v.ref != nullptr, r8, etab, minq4, w);
+                        for (uint32_t k = 0; k < 8; ++k) {
+                            const uint32_t qi = g + k;
+                            if (qi < lo || qi >= hi) continue;
+                            const uint32_t got = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu, want = E[qi] & 0x7f7fu;
+                            if (got != want || (((fm >> k) & 1u) != (want == 0 ? 1u : 0u))) {
+                                e->err = "emulation harness: ent_group8_swar differs from ent_plain at query index " + std::to_string(qi); return -1;
+                            }
+                        }
+                    }
+                }
             } else {
                 d.pad_ = (uint32_t)cursor; cursor += (size_t)(d.rend - d.rpos);
                 for (int32_t c = a; c < b; ++c) {
