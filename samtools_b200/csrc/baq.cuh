@@ -368,11 +368,8 @@ __global__ void __launch_bounds__(128) k_baq(RawSoA r, const BaqPlan *plan, cons
 // slab -- slot s of row i of lane l lives at ((i-1)*16 + s)*32 + l (16-byte units), so a warp store is one
 // contiguous 512-byte request -- and reads them back once, in reverse, through cp.async into a double-buffered
 // per-thread shared-memory stage one row ahead of the MAP step that consumes them.
-template <int K>
 struct BaqDevMem {
-    double2 *rows;             // this lane's slot 0 of row 1 (K > 0: of buffer row 0)
-    double2 *ckpt;             // K > 0: this lane's slot 0 of checkpoint 0 (24 slots per checkpoint)
-    double2 *parkp;            // K > 0: this lane's slot 0 of the parking row
+    double2 *rows;             // this lane's slot 0 of row 1
     int32_t *words;            // this lane's per-base scratch word 0
     double2 *stage;            // this thread's slot 0 of stage buffer 0 (shared memory)
     const uint8_t *refc; int64_t ref_lo, ref_n;
@@ -386,44 +383,13 @@ struct BaqDevMem {
         for (int k = 0; k < 8; ++k) w |= (uint64_t)((a + k >= 0 && a + k < ref_n) ? (refc[a + k] >> 4) : 4) << (8 * k);
         return w;
     }
-    __device__ __forceinline__ size_t row_of(int i) const { return (size_t)(K ? (i - 1) % (K ? K : 1) : i - 1) * (16 * 32); }
+    __device__ __forceinline__ size_t row_of(int i) const { return (size_t)(i - 1) * (16 * 32); }
     __device__ __forceinline__ void put_row(int i, const double (&M)[baqr::NB], const double (&I)[baqr::NB], double inv)
     {
         double2 *r = rows + row_of(i);
 #pragma unroll
         for (int j = 0; j < baqr::NB; ++j) r[j * 32] = make_double2(M[j], I[j]);
         reinterpret_cast<double *>(r + 15 * 32)[0] = inv;
-    }
-    // checkpoint s = forward row s*K+1 complete: slots 0..14 (M, I), 15..21 D pairs, 22 (D[14], 1/s), 23 the reference window
-    __device__ __forceinline__ void put_ckpt(int s, const double (&M)[baqr::NB], const double (&I)[baqr::NB], const double (&D)[baqr::NB], double inv, uint64_t win)
-    {
-        double2 *r = ckpt + (size_t)s * (24 * 32);
-#pragma unroll
-        for (int j = 0; j < baqr::NB; ++j) r[j * 32] = make_double2(M[j], I[j]);
-#pragma unroll
-        for (int j = 0; j < 7; ++j) r[(15 + j) * 32] = make_double2(D[2 * j], D[2 * j + 1]);
-        r[22 * 32] = make_double2(D[14], inv);
-        r[23 * 32] = make_double2(__longlong_as_double((long long)win), 0.);
-    }
-    __device__ __forceinline__ void get_ckpt(int s, double (&M)[baqr::NB], double (&I)[baqr::NB], double (&D)[baqr::NB], double &inv, uint64_t &win) const
-    {
-        const double2 *r = ckpt + (size_t)s * (24 * 32);
-#pragma unroll
-        for (int j = 0; j < baqr::NB; ++j) { const double2 v = r[j * 32]; M[j] = v.x; I[j] = v.y; }
-#pragma unroll
-        for (int j = 0; j < 7; ++j) { const double2 v = r[(15 + j) * 32]; D[2 * j] = v.x; D[2 * j + 1] = v.y; }
-        { const double2 v = r[22 * 32]; D[14] = v.x; inv = v.y; }
-        win = (uint64_t)__double_as_longlong(r[23 * 32].x);
-    }
-    __device__ __forceinline__ void park(const double (&M)[baqr::NB], const double (&I)[baqr::NB])
-    {
-#pragma unroll
-        for (int j = 0; j < baqr::NB; ++j) parkp[j * 32] = make_double2(M[j], I[j]);
-    }
-    __device__ __forceinline__ void unpark(double (&M)[baqr::NB], double (&I)[baqr::NB]) const
-    {
-#pragma unroll
-        for (int j = 0; j < baqr::NB; ++j) { const double2 v = parkp[j * 32]; M[j] = v.x; I[j] = v.y; }
     }
     __device__ __forceinline__ void fence() { __threadfence_block(); }
     __device__ __forceinline__ void fetch(int i)
@@ -457,12 +423,8 @@ __global__ void k_ref_codes(const char *ref, int64_t n, uint8_t *codes)
 constexpr int BAQR_THREADS = 128;
 constexpr int BAQR_STAGE_BYTES = 2 * 16 * BAQR_THREADS * 16;
 
-// K = 0: every forward row goes to the warp's slab (lqmax rows) and comes back once.  K > 0 (default 4): checkpoint mode
-// (baq_reg.h): the slab holds a K-row buffer + one parking row per warp (40 KB: the whole grid's buffers stay in L2), the
-// checkpoints (24 slots per K rows) go to a second array.
-template <int K>
 __global__ void __launch_bounds__(BAQR_THREADS, 3) k_baq_reg(RawSoA r, const BaqPlan *plan, const int32_t *idx, int64_t n_idx, double2 *slabs,
-                                                             unsigned long long slab_units, double2 *ckpts, unsigned long long ckpt_units, int lqmax, const uint8_t *refc,
+                                                             unsigned long long slab_units, int lqmax, const uint8_t *refc,
                                                              const double *q2p, const double *qthr, int extend)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -474,20 +436,17 @@ __global__ void __launch_bounds__(BAQR_THREADS, 3) k_baq_reg(RawSoA r, const Baq
     const int lane = threadIdx.x & 31;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_thr = (int64_t)gridDim.x * blockDim.x;
-    BaqDevMem<K> mem;
-    const size_t n_rows = K ? (size_t)K : (size_t)lqmax;
+    BaqDevMem mem;
     mem.rows = slabs + (size_t)gw * slab_units + lane;
-    mem.parkp = mem.rows + n_rows * (16 * 32);
-    mem.words = reinterpret_cast<int32_t *>(slabs + (size_t)gw * slab_units + (n_rows + (K ? 1 : 0)) * (16 * 32)) + lane;
-    mem.ckpt = ckpts ? ckpts + (size_t)gw * ckpt_units + lane : nullptr;
+    mem.words = reinterpret_cast<int32_t *>(slabs + (size_t)gw * slab_units + (size_t)lqmax * (16 * 32)) + lane;
     mem.stage = reinterpret_cast<double2 *>(s_dyn) + threadIdx.x;
     mem.refc = refc; mem.ref_n = r.ref_n;
     for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_idx; wi += n_thr) {
         const int64_t ri = idx[wi];
         const BaqPlan pl = plan[ri];
         mem.ref_lo = pl.xb - r.ref_beg;
-        baqr::baq_read<K>(mem, r.qual + r.qual_off[ri], r.seq4, (uint32_t)r.qual_off[ri], r.l_qseq[ri], pl.l_ref, r.pos[ri], pl.xb,
-                          r.cigar + r.cigar_off[ri], (int)r.n_cigar[ri], s_q2pf, s_qthr, extend != 0);
+        baqr::baq_read(mem, r.qual + r.qual_off[ri], r.seq4, (uint32_t)r.qual_off[ri], r.l_qseq[ri], pl.l_ref, r.pos[ri], pl.xb,
+                       r.cigar + r.cigar_off[ri], (int)r.n_cigar[ri], s_q2pf, s_qthr, extend != 0);
     }
 }
 
@@ -523,55 +482,19 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
     const int64_t n_idx = (int64_t)h[0], n_idx2 = (int64_t)h[3];
     if (n_idx2 > 0) {   // band 7: one thread per read, band row in registers
         const int lqmax = (int)h[4];
-        static const int ck = getenv("B200_BAQ_CKPT") ? atoi(getenv("B200_BAQ_CKPT")) : 0;      // 0: keep every forward row (default); 4: checkpoint mode (measured slower)
-        const int K = ck > 0 ? 4 : 0;
-        // per warp: the rows (lqmax, or K + a parking row) of 16 slots x 32 lanes x 16 B, then one scratch word per base and lane
-        const unsigned long long n_rows = K ? (unsigned long long)K + 1 : (unsigned long long)lqmax;
-        const unsigned long long slab_units = n_rows * (16 * 32) + ((unsigned long long)lqmax * 32 * 4 + 15) / 16 + 32;
-        const unsigned long long ckpt_units = K ? (unsigned long long)((lqmax + K - 1) / K) * (24 * 32) : 0;
+        // per warp: lqmax rows of 16 slots x 32 lanes x 16 B, then one scratch word per base and lane
+        const unsigned long long slab_units = (unsigned long long)lqmax * (16 * 32) + ((unsigned long long)lqmax * 32 * 4 + 15) / 16 + 32;
         int64_t warps = (int64_t)e->n_sm * 3 * (BAQR_THREADS / 32);
-        const int64_t cap = (int64_t)((24ULL << 30) / ((slab_units + ckpt_units) * 16));
+        const int64_t cap = (int64_t)((24ULL << 30) / (slab_units * 16));
         if (warps > cap) warps = cap;
         if (warps > (n_idx2 + 31) / 32) warps = (n_idx2 + 31) / 32;
         if (warps < 1) warps = 1;
         const int blocks = (int)((warps + BAQR_THREADS / 32 - 1) / (BAQR_THREADS / 32));
         warps = (int64_t)blocks * (BAQR_THREADS / 32);
         if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab_units * 2)) return -1;
-        if (K && ensure(e, e->baq_ck, e->cap_baq_ck, (size_t)warps * ckpt_units * 2)) return -1;
         static bool attr_set = false;
-        if (!attr_set) {
-            CK(cudaFuncSetAttribute(k_baq_reg<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BAQR_STAGE_BYTES));
-            CK(cudaFuncSetAttribute(k_baq_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BAQR_STAGE_BYTES));
-            attr_set = true;
-        }
-        if (K) {
-            // the K-row buffers are rewritten segment after segment: ask L2 to keep them (persisting access window on the stream)
-            static const int persist = getenv("B200_BAQ_PERSIST") ? atoi(getenv("B200_BAQ_PERSIST")) : 1;
-            cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-            if (persist) {
-                int max_persist = 0, max_win = 0;
-                cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
-                cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
-                const size_t bytes = (size_t)warps * slab_units * 16;
-                const size_t win = std::min<size_t>(bytes, (size_t)max_win);
-                const size_t keep = std::min<size_t>(win, (size_t)max_persist);
-                if (keep > 0) {
-                    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, keep);
-                    av.accessPolicyWindow.base_ptr = e->baq_f; av.accessPolicyWindow.num_bytes = win;
-                    av.accessPolicyWindow.hitRatio = (float)((double)keep / (double)win);
-                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-                    cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-                }
-            }
-            k_baq_reg<4><<<blocks, BAQR_THREADS, BAQR_STAGE_BYTES, e->stream>>>(r, plan, idx2, n_idx2, (double2 *)e->baq_f, slab_units, (double2 *)e->baq_ck, ckpt_units, lqmax, e->ref_codes, e->d_q2p, e->d_qthr, cf.baq != 3);
-            if (persist && av.accessPolicyWindow.num_bytes) {
-                av.accessPolicyWindow.num_bytes = 0;
-                cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-                cudaCtxResetPersistingL2Cache();
-            }
-        }
-        else k_baq_reg<0><<<blocks, BAQR_THREADS, BAQR_STAGE_BYTES, e->stream>>>(r, plan, idx2, n_idx2, (double2 *)e->baq_f, slab_units, nullptr, 0, lqmax, e->ref_codes, e->d_q2p, e->d_qthr, cf.baq != 3);
-        e->launches++;
+        if (!attr_set) { CK(cudaFuncSetAttribute(k_baq_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, BAQR_STAGE_BYTES)); attr_set = true; }
+        k_baq_reg<<<blocks, BAQR_THREADS, BAQR_STAGE_BYTES, e->stream>>>(r, plan, idx2, n_idx2, (double2 *)e->baq_f, slab_units, lqmax, e->ref_codes, e->d_q2p, e->d_qthr, cf.baq != 3); e->launches++;
         CK(cudaGetLastError());
     }
     if (n_idx > 0) {    // wide bands / long reads: one warp per read

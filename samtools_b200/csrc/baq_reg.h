@@ -145,16 +145,8 @@ PLP_HD int phred_of(double xx, const double *qthr)
 //   void wait(int pending)                       all but the `pending` most recent fetches have landed
 //   void get(int i, int j, double &fM, double &fI);   double inv(int i)
 //   void put_word(int j, int32_t w);  int32_t get_word(int j)        per-base scratch
-// Checkpoint mode (K > 0): the forward pass keeps only every K-th row (rows 1, K+1, 2K+1, ... with their D states and the
-// reference window), and the backward pass re-runs the forward recurrence over one K-row segment at a time into a K-row
-// buffer that is rewritten segment after segment -- small enough to live in L2 -- before it walks the segment backwards.
-// The recomputation starts from bit-identical inputs and evaluates the same expressions, so every stored value is the
-// one the single forward pass produced.  Costs the forward arithmetic twice (22 of 53 operations per cell), saves the
-// (l_query x 248 B) round trip through HBM.  put_row / fetch / get / inv then address row (i-1) % K of the buffer, and
-//   void put_ckpt(int s, M, I, D, double inv, uint64_t win);  void get_ckpt(int s, M, I, D, double &inv, uint64_t &win)
-//   void park(M, I);  void unpark(M, I)          backward state of the previous segment, out of the registers during a recomputation
 // q2pf[q] = (double)(float)pow(10, -q/10.)   qthr = break points (see baq.cuh)
-template <int K, class Mem>
+template <class Mem>
 PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff, int lq, int l_ref, int64_t pos, int64_t xb,
                      const uint32_t *cg, int n_cigar, const double *q2pf, const double *qthr, bool extend = true)
 {
@@ -180,7 +172,7 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         }
 #pragma unroll
         for (int j = BW; j < NB; ++j) if (cell_valid(1, j, l_ref)) { M[j] /= sum; I[j] /= sum; }
-        if (K == 0) mem.put_row(1, M, I, 1. / sum); else mem.put_ckpt(0, M, I, D, 1. / sum, win);
+        mem.put_row(1, M, I, 1. / sum);
         s_lq = sum;
     }
     // the inputs of a row (query base i-1, window position i + 6 entering at cell 14) come from the 8-row streams (see ld8)
@@ -211,11 +203,11 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
 #pragma unroll
             for (int j = 0; j < NB; ++j) if (cell_valid(i, j, l_ref)) { M[j] *= inv; I[j] *= inv; D[j] *= inv; }
         }
-        if (K == 0) mem.put_row(i, M, I, inv);
-        else if ((i - 1) % (K ? K : 1) == 0) mem.put_ckpt((i - 1) / (K ? K : 1), M, I, D, inv, win);
+        mem.put_row(i, M, I, inv);
         s_lq = sum;
     }
-    if (K == 0) mem.fence();
+    mem.fence();
+    mem.fetch(lq);
     double s_last = 0.;      // ---- termination
 #pragma unroll
     for (int j = 0; j < NB; ++j) if (cell_valid(lq, j, l_ref)) s_last += M[j] * p.sM + I[j] * p.sM;
@@ -234,52 +226,8 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         if (q0 >= 8) { qn = ld8(qual + q0 - 8); sn = ld8(sq + ((qpar + (uint32_t)q0 - 8u) >> 1)); }
         rw = mem.ref8(rb); if (rb >= 8) rn = mem.ref8(rb - 8);
     }
-    // the rows are walked in segments [i0, i1]: one segment (all rows) when every forward row was kept, K-row segments
-    // re-derived from their checkpoint otherwise
-    const int nseg = K ? (lq + (K ? K : 1) - 1) / (K ? K : 1) : 1;
-    for (int sgm = nseg - 1; sgm >= 0; --sgm) {
-    const int i0 = K ? sgm * K + 1 : 1, i1 = K ? (i0 + K - 1 < lq ? i0 + K - 1 : lq) : lq;
-    if (K) {
-        // ---- forward rows i0 .. i1 again, from the checkpoint of row i0, into the segment buffer
-        const bool parked = true;      // the backward state (for the last segment: its initial values) leaves the registers while the forward rows are re-derived
-        const uint64_t qv = ld8(qual + i0), sv = ld8(sq + ((qpar + (uint32_t)i0) >> 1));     // query bases i0 .. i0+7 (rows i0+1 ..)
-        if (parked) mem.park(M, I);
-        {
-            double fM[NB], fI[NB], fD[NB]; double finv; uint64_t fwin;
-            mem.get_ckpt(sgm, fM, fI, fD, finv, fwin);
-            mem.put_row(i0, fM, fI, finv);
-#pragma unroll 1
-            for (int i = i0 + 1; i <= i1; ++i) {                 // one copy of the row code (the kernel is instruction-cache bound otherwise)
-                {
-                    const int qi = i - 1, rp = i + BW - 1;
-                    const int crr = rp < l_ref ? mem.ref_code(rp) : 4;
-                    fwin = (fwin >> 4) | ((uint64_t)crr << (4 * (NB - 1)));
-                    const int qc = plp::nt16_int_of(nib_at(sv, qpar, i0, qi));
-                    const double ql = q2pf[byte_of(qv, qi - i0)];
-                    const double em_match = qc > 3 ? 1. : 1. - ql, em_mis = qc > 3 ? 1. : ql * BAQR_EM;
-                    const uint64_t xw = fwin ^ (kRep * (uint64_t)(qc & 7));
-                    double sum;
-                    if (i > BW && i + BW <= l_ref) {
-                        sum = fwd_row<false>(fM, fI, fD, p, xw, em_match, em_mis, i, l_ref);
-                        finv = 1. / sum;
-#pragma unroll
-                        for (int j = 0; j < NB; ++j) { fM[j] *= finv; fI[j] *= finv; fD[j] *= finv; }
-                    } else {
-                        sum = fwd_row<true>(fM, fI, fD, p, xw, em_match, em_mis, i, l_ref);
-                        finv = 1. / sum;
-#pragma unroll
-                        for (int j = 0; j < NB; ++j) if (cell_valid(i, j, l_ref)) { fM[j] *= finv; fI[j] *= finv; fD[j] *= finv; }
-                    }
-                    mem.put_row(i, fM, fI, finv);
-                }
-            }
-        }
-        mem.fence();
-        if (parked) mem.unpark(M, I);
-    }
-    mem.fetch(i1);
-    for (int i = i1; i >= i0; --i) {
-        if (i > i0) mem.fetch(i - 1);
+    for (int i = lq; i >= 1; --i) {
+        if (i > 1) mem.fetch(i - 1);
         if (i < lq) {
             const int qi = i, rp = i - BW;
             if ((qi & 7) == 7 && qi != lq - 1) { qw = qn; sw = sn; if (qi >= 15) { qn = ld8(qual + qi - 15); sn = ld8(sq + ((qpar + (uint32_t)qi - 15u) >> 1)); } }
@@ -293,20 +241,20 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
             const uint64_t xw = win ^ (kRep * (uint64_t)(qc & 7));
             if (i > BW && i + BW < l_ref) {
                 bwd_row<false>(M, I, p, xw, em_match, em_mis, i, l_ref);
-                mem.wait(i > i0 ? 1 : 0);                            // row i (fetched one iteration ago) has landed
+                mem.wait(1);                                         // row i (fetched one iteration ago) has landed
                 const double ys = mem.inv(i);
 #pragma unroll
                 for (int j = 0; j < NB; ++j) { M[j] *= ys; I[j] *= ys; }
             } else {
                 bwd_row<true>(M, I, p, xw, em_match, em_mis, i, l_ref);
-                mem.wait(i > i0 ? 1 : 0);
+                mem.wait(i > 1 ? 1 : 0);
                 const double ys = mem.inv(i);
 #pragma unroll
                 for (int j = 0; j < NB; ++j) if (cell_valid(i, j, l_ref)) { M[j] *= ys; I[j] *= ys; }
             }
         } else {
             // row lq: nothing to compute (the streams are primed above)
-            mem.wait(i > i0 ? 1 : 0);
+            mem.wait(i > 1 ? 1 : 0);
         }
         // ---- MAP of row i (cells outside the band are zero on both sides: they add 0 and never exceed the maximum)
         double sum = 0., mx = 0.; int best = -1;
@@ -322,7 +270,6 @@ PLP_HD void baq_read(Mem &mem, uint8_t *qual, const uint8_t *seq4, uint32_t qoff
         const int kq = phred_of(1. - mx, qthr);
         mem.put_word(i - 1, (int32_t)((uint32_t)max_k << 8 | (uint32_t)kq));
     }
-    }   // segments
     // ---- sam_prob_realn epilogue (APPLY): per match run, zero the bases whose MAP state is not the aligned match,
     // with EXTEND replace each by the smaller of the running maxima from both ends of the run, cap the quality
     int64_t x = pos; int y = 0;

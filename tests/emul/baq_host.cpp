@@ -15,24 +15,7 @@ extern "C" {
 
 struct HostMem {
     const char *ref; int64_t ref_len, xb;
-    int K = 0;                                    // 0: every forward row kept; > 0: checkpoint mode, rows live in a K-row buffer
     std::vector<double> fm, fi, iv; std::vector<int32_t> w;
-    std::vector<double> ck; std::vector<uint64_t> ckw; double pk[2 * baqr::NB];
-    int slot(int i) const { return K ? (i - 1) % K : i; }
-    void put_ckpt(int s, const double (&M)[baqr::NB], const double (&I)[baqr::NB], const double (&D)[baqr::NB], double inv, uint64_t win)
-    {
-        double *c = &ck[(size_t)s * (3 * baqr::NB + 1)];
-        for (int j = 0; j < baqr::NB; ++j) { c[j] = M[j]; c[baqr::NB + j] = I[j]; c[2 * baqr::NB + j] = D[j]; }
-        c[3 * baqr::NB] = inv; ckw[s] = win;
-    }
-    void get_ckpt(int s, double (&M)[baqr::NB], double (&I)[baqr::NB], double (&D)[baqr::NB], double &inv, uint64_t &win) const
-    {
-        const double *c = &ck[(size_t)s * (3 * baqr::NB + 1)];
-        for (int j = 0; j < baqr::NB; ++j) { M[j] = c[j]; I[j] = c[baqr::NB + j]; D[j] = c[2 * baqr::NB + j]; }
-        inv = c[3 * baqr::NB]; win = ckw[s];
-    }
-    void park(const double (&M)[baqr::NB], const double (&I)[baqr::NB]) { for (int j = 0; j < baqr::NB; ++j) { pk[j] = M[j]; pk[baqr::NB + j] = I[j]; } }
-    void unpark(double (&M)[baqr::NB], double (&I)[baqr::NB]) const { for (int j = 0; j < baqr::NB; ++j) { M[j] = pk[j]; I[j] = pk[baqr::NB + j]; } }
     int ref_code(int p) const
     {
         const int64_t a = xb + p;
@@ -42,15 +25,14 @@ struct HostMem {
     uint64_t ref8(int p) const { uint64_t w = 0; for (int k = 0; k < 8; ++k) w |= (uint64_t)ref_code(p + k) << (8 * k); return w; }
     void put_row(int i, const double (&M)[baqr::NB], const double (&I)[baqr::NB], double inv)
     {
-        const int r = slot(i);
-        for (int j = 0; j < baqr::NB; ++j) { fm[(size_t)r * baqr::NB + j] = M[j]; fi[(size_t)r * baqr::NB + j] = I[j]; }
-        iv[r] = inv;
+        for (int j = 0; j < baqr::NB; ++j) { fm[(size_t)i * baqr::NB + j] = M[j]; fi[(size_t)i * baqr::NB + j] = I[j]; }
+        iv[i] = inv;
     }
     void fence() {}
     void fetch(int) {}
     void wait(int) {}
-    void get(int i, int j, double &a, double &b) const { const int r = slot(i); a = fm[(size_t)r * baqr::NB + j]; b = fi[(size_t)r * baqr::NB + j]; }
-    double inv(int i) const { return iv[slot(i)]; }
+    void get(int i, int j, double &a, double &b) const { a = fm[(size_t)i * baqr::NB + j]; b = fi[(size_t)i * baqr::NB + j]; }
+    double inv(int i) const { return iv[i]; }
     void put_word(int j, int32_t x) { w[j] = x; }
     int32_t get_word(int j) const { return w[j]; }
 };
@@ -107,20 +89,13 @@ int main(int argc, char **argv)
         }
         if (fast) {
             ++n_fast;
+            HostMem mem; mem.ref = ref; mem.ref_len = ref_len; mem.xb = xb;
+            mem.fm.assign((size_t)(lq + 2) * baqr::NB, 0.); mem.fi = mem.fm; mem.iv.assign(lq + 2, 0.); mem.w.assign(lq + 1, 0);
+            std::vector<uint8_t> q(r.qual, r.qual + lq);
+            q.resize((size_t)lq + 16, 0);                                  // ld8 slack (the staged device arrays carry it too)
             std::vector<uint8_t> sq(r.seq, r.seq + (lq + 1) / 2);
             sq.resize(sq.size() + 16, 0);
-            std::vector<uint8_t> q;
-            for (int mode = 0; mode < 3; ++mode) {            // every forward row kept / checkpoints every 4 rows / every 3 rows: all must agree with the oracle
-                HostMem mem; mem.ref = ref; mem.ref_len = ref_len; mem.xb = xb; mem.K = mode == 0 ? 0 : (mode == 1 ? 4 : 3);
-                mem.fm.assign((size_t)(lq + 2) * baqr::NB, 0.); mem.fi = mem.fm; mem.iv.assign(lq + 2, 0.); mem.w.assign(lq + 1, 0);
-                mem.ck.assign((size_t)(lq + 2) * (3 * baqr::NB + 1), 0.); mem.ckw.assign(lq + 2, 0);
-                q.assign(r.qual, r.qual + lq);
-                q.resize((size_t)lq + 16, 0);                                  // ld8 slack (the staged device arrays carry it too)
-                if (mode == 0) baqr::baq_read<0>(mem, q.data(), sq.data(), 0u, lq, (int)l_ref, r.pos, xb, r.cigar, (int)r.n_cigar, q2pf, qthr);
-                else if (mode == 1) baqr::baq_read<4>(mem, q.data(), sq.data(), 0u, lq, (int)l_ref, r.pos, xb, r.cigar, (int)r.n_cigar, q2pf, qthr);
-                else baqr::baq_read<3>(mem, q.data(), sq.data(), 0u, lq, (int)l_ref, r.pos, xb, r.cigar, (int)r.n_cigar, q2pf, qthr);
-                if (memcmp(q.data(), want.qual, lq) != 0) break;
-            }
+            baqr::baq_read(mem, q.data(), sq.data(), 0u, lq, (int)l_ref, r.pos, xb, r.cigar, (int)r.n_cigar, q2pf, qthr);
             if (memcmp(q.data(), want.qual, lq) != 0) {
                 if (++bad <= 5) {
                     fprintf(stderr, "MISMATCH read %s pos %lld lq %d l_ref %lld\n", r.qname, (long long)r.pos, lq, (long long)l_ref);
