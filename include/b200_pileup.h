@@ -21,6 +21,7 @@
  *                         print_empty_pileup / -a gaps    bam_plcmd.c:372-398, :610-660, :880-910
  *   b200_depth_text()     add_depth + flush rows          bam2depth.c:209-477, zero_region :88-118
  *   b200_coverage()       column reducers                 coverage.c:589-661
+ *   b200_coverage_hist()  per-bin counters of -m / -D     coverage.c:609-660
  *   b200_bedcov()         per-interval column reducers    bedcov.c:303-331
  *   b200_glf()            bcf_call_glfgen + errmod_cal    bam2bcf.c:65-123 (+ htslib errmod.c)
  *   b200_pileup_entries() bam_plp64_next/resolve_cigar2   (htslib sam.c) -> arrays of bam_pileup1_t fields
@@ -193,6 +194,12 @@ int b200_depth_text(b200_engine_t *e, const b200_depth_conf_t *conf, char *out, 
 uint64_t b200_mpileup_text_bound(const b200_engine_t *e, const b200_mpileup_conf_t *conf);
 uint64_t b200_depth_text_bound(const b200_engine_t *e);
 int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *conf, b200_coverage_sums_t *sums);
+/* the per-bin counters behind `coverage -m / -D` (coverage.c:609-660): column `pos` of the staged window adds to bin
+ * (pos - beg) / bin_width (bins >= n_bins are dropped) either 1 when the column counts as covered (plot_depth == 0: breadth)
+ * or its filtered depth summed over the files (plot_depth != 0).  hist[n_bins] is ADDED to (32-bit wrap, like the
+ * reference's uint32_t counters), so the windows of one reference sequence accumulate. */
+int b200_coverage_hist(b200_engine_t *e, const b200_coverage_conf_t *conf, int64_t beg, int64_t bin_width, int32_t n_bins,
+                       int32_t plot_depth, uint32_t *hist);
 /* bedcov reducers (bedcov.c:316-331) over the staged window [beg,end): per input file the sum of the per-column depth --
  * without deletions and reference skips when skip_del_refskip or min_depth >= 0, as the reference does -- and, for
  * min_depth >= 0, the number of columns whose depth reaches it (pcov may be NULL).  Stage with B200_MODE_COVERAGE

@@ -464,6 +464,19 @@ __global__ void __launch_bounds__(256) k_coverage(View v, int32_t min_baseQ, int
     }
 }
 
+// per-bin counters of the histogram views (coverage.c:609-660): breadth (covered columns) or depth per bin
+__global__ void __launch_bounds__(256) k_coverage_hist(View v, int32_t min_baseQ, int32_t min_depth, int64_t beg_rel, int64_t bin_width, int32_t n_bins,
+                                                       int plot_depth, uint32_t *hist)
+{
+    const int32_t c = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= v.ncols) return;
+    CvCol o; cv_column(v, min_baseQ, c >> 5, c, o);
+    const uint32_t add = plot_depth ? o.depth : ((o.count_base && o.depth >= (uint32_t)min_depth) ? 1u : 0u);
+    if (!add) return;
+    const int64_t bin = ((int64_t)c - beg_rel) / bin_width;
+    if (bin >= 0 && bin < n_bins) atomicAdd(&hist[bin], add);
+}
+
 // bedcov column reducers (bedcov.c:316-331) over the staged window, per input file: sum of the per-column depth (optionally
 // without deletions / reference skips) and the number of columns at or above a depth threshold.  A column takes part when
 // the multi-file iterator would return it, i.e. when any file has a read over it.
@@ -1207,6 +1220,24 @@ extern "C" int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b2
     CK(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1); e->last_kernel_ms = ms;
     sums->n_covered_bases = h[0]; sums->summed_coverage = h[1]; sums->summed_baseQ = h[2]; sums->quality_bases = h[3]; sums->missing_qual = h[4];
+    return 0;
+}
+
+extern "C" int b200_coverage_hist(b200_engine_t *e, const b200_coverage_conf_t *c, int64_t beg, int64_t bin_width, int32_t n_bins, int32_t plot_depth, uint32_t *hist)
+{
+    if (!e || !e->staged) { if (e) snprintf(e->err, sizeof e->err, "no staged batch"); return -1; }
+    if (!c || !hist || n_bins <= 0 || bin_width <= 0) { snprintf(e->err, sizeof e->err, "bad histogram arguments"); return -1; }
+    CK(cudaSetDevice(e->device));
+    View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);
+    if (v.ncols <= 0) return 0;
+    ENSURE(gl_n, (size_t)n_bins + 1);                     // int32 scratch shared with the GL path (never live at the same time)
+    CK(cudaMemsetAsync(e->gl_n, 0, (size_t)n_bins * 4, e->stream));
+    k_coverage_hist<<<nblk(v.ncols, 256), 256, 0, e->stream>>>(v, c->min_baseQ, c->min_depth, beg - e->win_base, bin_width, n_bins, plot_depth != 0, (uint32_t *)e->gl_n); e->launches++;
+    std::vector<uint32_t> h((size_t)n_bins);
+    CK(cudaMemcpyAsync(h.data(), e->gl_n, (size_t)n_bins * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+    for (int32_t k = 0; k < n_bins; ++k) hist[k] += h[(size_t)k];
     return 0;
 }
 

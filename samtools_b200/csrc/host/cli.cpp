@@ -11,10 +11,12 @@
 // the GPU; there is no CPU fallback (engine creation fails without a device).
 //
 // Not offered on the device path yet: -M/--output-mods,
-// --output-QNAME, --output-extra; coverage histograms (-m/-A/-D/-w, terminal UI).
+// (none here any more: host string columns and the coverage histogram views are served from device results too).
 #include "hts_io.hpp"
 #include "packer.hpp"
 #include <getopt.h>
+#include <sys/ioctl.h>
+#include <math.h>
 #include <zlib.h>
 #include <cctype>
 #include <climits>
@@ -687,6 +689,9 @@ int main_coverage(int argc, char **argv)
     int fail_flags = F_UNMAP | F_SECONDARY | F_QCFAIL | F_DUP, required_flags = 0;
     const char *reg = nullptr, *file_list = nullptr, *out_fn = nullptr;
     bool print_header = true;
+    // histogram views (coverage.c:391-402): -m, -A (ASCII glyphs), -D (depth instead of breadth), -w bins
+    bool want_hist = false, utf = true, plot_depth = false, full_width = true;
+    int n_bins_opt = 50;
     static const struct option lo[] = { {"rf", 1, 0, 1}, {"ff", 1, 0, 2}, {"incl-flags", 1, 0, 1}, {"excl-flags", 1, 0, 2},
         {"bam-list", 1, 0, 'b'}, {"min-read-len", 1, 0, 'l'}, {"min-MQ", 1, 0, 'q'}, {"min-mq", 1, 0, 'q'}, {"min-BQ", 1, 0, 'Q'},
         {"min-bq", 1, 0, 'Q'}, {"histogram", 0, 0, 'm'}, {"ascii", 0, 0, 'A'}, {"plot-depth", 0, 0, 'D'}, {"output", 1, 0, 'o'},
@@ -699,7 +704,7 @@ int main_coverage(int argc, char **argv)
         case 1: if ((required_flags = parse_flag(optarg)) < 0) { fprintf(stderr, "Could not parse --rf %s\n", optarg); return 1; } break;
         case 2: if ((fail_flags = parse_flag(optarg)) < 0) { fprintf(stderr, "Could not parse --ff %s\n", optarg); return 1; } break;
         case 3: if ((i = atoi(optarg)) > 0) mindepth = i; break;
-        case 'o': out_fn = optarg; break;
+        case 'o': out_fn = optarg; full_width = false; break;
         case 'l': min_len = atoi(optarg); break;
         case 'q': min_mapQ = atoi(optarg); break;
         case 'Q': min_baseQ = atoi(optarg); break;
@@ -707,10 +712,18 @@ int main_coverage(int argc, char **argv)
         case 'r': reg = optarg; break;
         case 'b': file_list = optarg; break;
         case 'H': print_header = false; break;
-        case 'm': case 'A': case 'D': case 'w':
-            fprintf(stderr, "b200samtools coverage: histogram views are terminal UI and not provided; tabular output only\n"); return 1;
+        case 'm': want_hist = true; break;
+        case 'A': utf = false; want_hist = true; break;
+        case 'D': plot_depth = true; want_hist = true; break;
+        case 'w': n_bins_opt = atoi(optarg); full_width = false; want_hist = true; break;
         default: fprintf(stderr, "Usage: samtools coverage [options] in1.bam [in2.bam [...]]\n"); return 1;
         }
+    }
+    if (n_bins_opt <= 0 || full_width) {     // terminal width - 40, at least 40 (coverage.c:437-461)
+        int columns = 0;
+        if (const char *ec = getenv("COLUMNS")) columns = atoi(ec);
+        else { struct winsize ws; if (ioctl(2, TIOCGWINSZ, &ws) == 0) columns = ws.ws_col; }
+        n_bins_opt = columns > 60 ? columns - 40 : 40;
     }
     std::vector<std::string> fn;
     if (file_list) { if (!read_file_list(file_list, fn)) return 1; }
@@ -730,7 +743,7 @@ int main_coverage(int argc, char **argv)
     Engine eng;
     if (!eng.init()) return 1;
     const int nref = h.n_ref();
-    struct Row { b200_coverage_sums_t s; uint64_t n_sel = 0, sum_mq = 0; bool covered = false; int64_t beg = 0, end = 0; };
+    struct Row { b200_coverage_sums_t s; uint64_t n_sel = 0, sum_mq = 0, n_reads = 0; bool covered = false; int64_t beg = 0, end = 0, bin_width = 1; int n_bins = 0; std::vector<uint32_t> hist; };
     std::vector<Row> rows((size_t)nref);
     b200_stage_conf_t sc; memset(&sc, 0, sizeof sc);
     sc.mode = B200_MODE_COVERAGE; sc.rflag_filter = fail_flags; sc.rflag_require = required_flags; sc.min_mq = min_mapQ; sc.c_min_len = min_len;
@@ -744,6 +757,12 @@ int main_coverage(int argc, char **argv)
         memset(&rw.s, 0, sizeof rw.s);
         rw.beg = 0; rw.end = h.lens[(size_t)tid];
         if (reg && tid == tid0) { rw.beg = beg0; rw.end = end0 == POS_MAX ? h.lens[(size_t)tid] : end0; }
+        if (want_hist) {      // bins of this reference sequence (coverage.c:552-563, :609-610)
+            const int64_t span = rw.end - rw.beg;
+            int64_t nb = (int64_t)n_bins_opt > span ? span : (int64_t)n_bins_opt;
+            rw.n_bins = (int)nb; rw.bin_width = span / (nb > 0 ? nb : 1);
+            rw.hist.assign((size_t)(nb > 0 ? nb : 0), 0u);
+        }
         bool has = false;
         for (i = 0; i < nfn; ++i) { if (!load_tid(fd[(size_t)i], tid, "coverage")) return 1; if (tid < (int)fd[(size_t)i].by_tid.size() && !fd[(size_t)i].by_tid[(size_t)tid].empty()) has = true; }
         if (!has) continue;
@@ -769,7 +788,7 @@ int main_coverage(int argc, char **argv)
             sc.beg = wb; sc.end = we;
             b200_stage_stats_t st;
             if (b200_stage(eng.e, &batch, &sc, &st) != 0) { fprintf(stderr, "samtools coverage: %s\n", b200_last_error(eng.e)); return 1; }
-            rw.n_sel += st.n_selected_reads; rw.sum_mq += st.summed_mapq;
+            rw.n_sel += st.n_selected_reads; rw.sum_mq += st.summed_mapq; rw.n_reads += st.n_reads;
             // a column exists as soon as one kept read has a non-empty reference span (before the region test)
             if (st.n_kept > 0) {
                 b200_coverage_sums_t ws;
@@ -778,6 +797,8 @@ int main_coverage(int argc, char **argv)
                 rw.s.quality_bases += ws.quality_bases; rw.s.missing_qual += ws.missing_qual;
                 if (!rw.covered) { rw.covered = true; order.push_back(tid); }   // refined: zero-span-only contigs are vanishingly rare
                 if (ws.missing_qual) warn = true;
+                if (want_hist && rw.n_bins > 0 && rw.bin_width > 0 &&
+                    b200_coverage_hist(eng.e, &cc, rw.beg, rw.bin_width, rw.n_bins, plot_depth ? 1 : 0, rw.hist.data()) != 0) { fprintf(stderr, "samtools coverage: %s\n", b200_last_error(eng.e)); return 1; }
             }
             if (last_w) break;
         }
@@ -792,9 +813,75 @@ int main_coverage(int argc, char **argv)
                 r.s.quality_bases > 0 ? r.s.summed_baseQ / (double)r.s.quality_bases : 0,
                 r.n_sel > 0 ? r.sum_mq / (double)r.n_sel : 0);
     };
-    for (int tid : order) print_row(tid);
-    if (order.empty() && reg && *reg != '*' && tid0 >= 0) print_row(tid0);
-    if (!reg) for (int tid = 0; tid < nref; ++tid) if (!rows[(size_t)tid].covered) print_row(tid);
+    // ---- histogram view (coverage.c:223-304): ten rows of block glyphs over the bins, the row's statistic to the right
+    auto fmt_bp = [](double bp, char *buf) -> char * {
+        static const char *unit[] = {"", "K", "M", "G", "T"};
+        int u = 0;
+        for (; bp >= 1000 && u < 4; ++u) bp /= 1000;
+        snprintf(buf, 48, "%.*f%s", u, bp, unit[u]);
+        return buf;
+    };
+    auto centred = [](const char *t, char *buf, int width) -> char * {
+        const int len = (int)strlen(t), pad = (width - len) / 2, odd = (width - len) % 2;
+        if (pad >= 1) snprintf(buf, 96, " %*s%*s", len + pad, t, pad - 1 + odd, " ");
+        else snprintf(buf, 96, "%s", t);
+        return buf;
+    };
+    auto print_hist = [&](int tid) {
+        static const char *const g8[8] = {"\xE2\x96\x81", "\xE2\x96\x82", "\xE2\x96\x83", "\xE2\x96\x84", "\xE2\x96\x85", "\xE2\x96\x86", "\xE2\x96\x87", "\xE2\x96\x88"};
+        static const char *const g2[2] = {".", ":"};
+        const Row &r = rows[(size_t)tid];
+        const int n_rows = 10, steps = utf ? 8 : 2, nb = r.n_bins;
+        const char *const *glyph = utf ? g8 : g2;
+        const char *bar = utf ? "\xE2\x94\x82" : "|";
+        const double region_len = (double)(r.end - r.beg);
+        std::vector<double> val((size_t)std::max(nb, 1), 0.0);
+        double top = 0.0;
+        for (int k = 0; k < nb; ++k) {
+            val[(size_t)k] = (uint32_t)((plot_depth ? 1u : 100u) * r.hist[(size_t)k]) / (double)r.bin_width;   // 32-bit product, like the reference
+            top = std::max(top, val[(size_t)k]);
+        }
+        char b1[64], b2[128];
+        fprintf(fp, "%s (%sbp)\n", h.names[(size_t)tid].c_str(), fmt_bp((double)h.lens[(size_t)tid], b1));
+        const double step = top / n_rows;
+        for (int row = n_rows - 1; row >= 0; --row) {
+            const double base = step * row;
+            if (plot_depth) fprintf(fp, ">%8.1f ", row * step); else fprintf(fp, ">%7.2f%% ", base);
+            fputs(bar, fp);
+            for (int k = 0; k < nb; ++k) {
+                int g = steps - 1;                      // all-zero histogram: the reference divides 0 by 0; its x86-64 build prints the full block
+                if (step != 0.0) { g = (int)round(steps * (val[(size_t)k] - base) / step) - 1; if (g >= steps) g = steps - 1; }
+                if (g < 0) fputc(' ', fp); else fputs(glyph[g], fp);
+            }
+            fputs(bar, fp); fputc(' ', fp);
+            const unsigned n_sel = (unsigned)r.n_sel, n_all = (unsigned)r.n_reads;
+            switch (row) {
+            case 9: fprintf(fp, "Number of reads: %u", n_sel); break;
+            case 8: if (n_all - n_sel > 0) fprintf(fp, "    (%i filtered)", (int)(n_all - n_sel)); break;
+            case 7: fprintf(fp, "Covered bases:   %sbp", fmt_bp((double)r.s.n_covered_bases, b1)); break;
+            case 6: fprintf(fp, "Percent covered: %.4g%%", 100.0 * r.s.n_covered_bases / region_len); break;
+            case 5: fprintf(fp, "Mean coverage:   %.3gx", r.s.summed_coverage / region_len); break;
+            case 4: fprintf(fp, "Mean baseQ:      %.3g", r.s.quality_bases > 0 ? r.s.summed_baseQ / (double)r.s.quality_bases : 0); break;
+            case 3: fprintf(fp, "Mean mapQ:       %.3g", r.sum_mq / (double)r.n_sel); break;
+            case 1: fprintf(fp, "Histo bin width: %sbp", fmt_bp((double)r.bin_width, b1)); break;
+            case 0: if (plot_depth) fprintf(fp, "Histo max cov:   %.5g", top); else fprintf(fp, "Histo max bin:   %.5g%%", top); break;
+            default: break;
+            }
+            fputc('\n', fp);
+        }
+        fprintf(fp, "     %s", centred(fmt_bp((double)(r.beg + 1), b1), b2, 10));
+        for (int k = 10; k < 10 * (nb / 10); k += 10) fprintf(fp, "%s", centred(fmt_bp((double)(r.beg + r.bin_width * k), b1), b2, 10));
+        fprintf(fp, "%*s%s", nb % 10, " ", centred(fmt_bp((double)r.end, b1), b2, 10));
+        fputc('\n', fp);
+    };
+    if (want_hist) {     // one block per reference sequence that has columns, blank line between blocks (coverage.c:592-597, :672-675)
+        for (size_t k = 0; k < order.size(); ++k) { if (k) fputc('\n', fp); print_hist(order[k]); }
+        if (order.empty() && reg && *reg != '*' && tid0 >= 0) print_hist(tid0);
+    } else {
+        for (int tid : order) print_row(tid);
+        if (order.empty() && reg && *reg != '*' && tid0 >= 0) print_row(tid0);
+        if (!reg) for (int tid = 0; tid < nref; ++tid) if (!rows[(size_t)tid].covered) print_row(tid);
+    }
     if (warn) fprintf(stderr, "samtools coverage: Warning:  Missing quality values in alignments.  Mean base quality calculated only on available values.\n");
     if (fp != stdout) fclose(fp); else fflush(fp);
     return 0;

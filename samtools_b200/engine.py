@@ -17,7 +17,7 @@ RB_HOST_SKIP, RB_NAME_ODD, RB_BAQ_DONE = 1, 2, 4
 POS_MAX = (0x7fffffff << 32) | 0xffffffff
 
 EXPORTS = ['b200_engine_create', 'b200_engine_destroy', 'b200_last_error', 'b200_version', 'b200_stage',
-           'b200_mpileup_text', 'b200_depth_text', 'b200_coverage', 'b200_glf', 'b200_fetch_qual',
+           'b200_mpileup_text', 'b200_depth_text', 'b200_coverage', 'b200_coverage_hist', 'b200_glf', 'b200_fetch_qual',
            'b200_fetch_mapq_keep', 'b200_pileup_entries', 'b200_last_kernel_ms', 'b200_last_stage_ms', 'b200_set_keep_raw', 'b200_restage', 'b200_last_stage_device_ms',
            'b200_launch_count', 'b200_last_mpileup_parts_ms', 'b200_gl_rng_draws', 'b200_last_baq_ms',
            'b200_errmod_cal', 'b200_glfgen', 'b200_cap_mapq', 'b200_mpileup_text_bound', 'b200_depth_text_bound', 'b200_bedcov']

@@ -352,6 +352,17 @@ int b200_coverage(b200_engine_t *e, const b200_coverage_conf_t *c, b200_coverage
     }
     return 0;
 }
+int b200_coverage_hist(b200_engine_t *e, const b200_coverage_conf_t *c, int64_t beg, int64_t bin_width, int32_t n_bins, int32_t plot_depth, uint32_t *hist)
+{
+    View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);
+    for (int32_t col = 0; col < v.ncols; ++col) {
+        CvCol o; cv_column(v, c->min_baseQ, col >> 5, col, o);
+        const uint32_t add = plot_depth ? o.depth : ((o.count_base && o.depth >= (uint32_t)c->min_depth) ? 1u : 0u);
+        const int64_t bin = ((int64_t)col - (beg - v.win_base)) / bin_width;
+        if (add && bin >= 0 && bin < n_bins) hist[bin] += add;
+    }
+    return 0;
+}
 int b200_bedcov(b200_engine_t *e, int32_t skip_dn, int32_t min_depth, uint64_t *cnt, uint64_t *pcov)
 {
     View v; fill_view(e, v, nullptr, nullptr, 0, 0, 0);

@@ -59,3 +59,15 @@ def test_column_windows_with_halo(emul_bin, oracle_bin, corpus, monkeypatch):
     with ThreadPoolExecutor(max_workers=6) as ex:
         bad = [r for r in ex.map(run, todo) if r]
     assert not bad, bad[:3]
+
+
+def test_coverage_histogram_views(emul_bin, oracle_bin, corpus, tmp_path, monkeypatch):
+    """`coverage -m / -A / -D / -w` (per-bin counters b200_coverage_hist + the host-side print_hist) against the oracle, on the
+    reference's sample.sam and on a synthetic 30 kb contig cut into 997-column windows (bins accumulate across windows)."""
+    import hist_cases
+    from samtools_b200 import synth
+    soa = synth.make_batch(length=30_000, depth=12, seed=21)
+    sam = str(tmp_path / 'h.sam')
+    synth.write_sam(sam, soa)
+    assert not hist_cases.run_all(emul_bin, oracle_bin, corpus, tmp_path, sam)
+    assert not hist_cases.run_all(emul_bin, oracle_bin, corpus, tmp_path, sam, {'B200_WINDOW_COLS': '997'})

@@ -392,3 +392,15 @@ def test_c1_ex1_engine_vs_oracle(cmd, cli, oracle_bin, corpus):
     got = subprocess.run(f'{cli} {cmd}', shell=True, cwd=cwd, capture_output=True)
     assert got.returncode == 0 and len(want.stdout) > 1000
     assert got.stdout == want.stdout
+
+
+# ---------------------------------------------------------------- coverage histogram views (coverage.c:223-304, 609-660)
+def test_coverage_histogram_views_on_gpu(cli, oracle_bin, corpus, tmp_path):
+    """per-bin breadth / depth counters on the device (k_coverage_hist), print_hist on the host; oracle-compared (unpinned)"""
+    import hist_cases
+    from samtools_b200 import synth
+    soa = synth.make_batch(length=30_000, depth=12, seed=21)
+    sam = str(tmp_path / 'h.sam')
+    synth.write_sam(sam, soa)
+    assert not hist_cases.run_all(cli, oracle_bin, corpus, tmp_path, sam)
+    assert not hist_cases.run_all(cli, oracle_bin, corpus, tmp_path, sam, {'B200_WINDOW_COLS': '997'})
