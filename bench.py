@@ -57,6 +57,23 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(kernels):
+    """DRAM bytes per launch of the named kernels from the round's ncu capture (profiles/r02_traffic.json, written by
+    tools/ncu_traffic.py) -- only while the kernel sources are the ones the capture was taken from; otherwise None."""
+    p = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+    try:
+        import hashlib
+        rec = json.load(open(p))
+        h = hashlib.sha256()
+        for s_ in rec['sources']:
+            h.update(open(os.path.join(ROOT, s_), 'rb').read())
+        if h.hexdigest() != rec['sources_sha256']:
+            return None
+        return float(sum(rec['dram_bytes_per_launch'][k] for k in kernels))
+    except Exception:
+        return None
+
+
 def usable_cores():
     """CPUs this process may really use: scheduler affinity capped by the cgroup CPU quota."""
     try:
@@ -281,7 +298,7 @@ def main():
     ap.add_argument('--region-mb', type=float, default=8.0)
     ap.add_argument('--modes', default='all', help="comma list of extra workloads (%s), 'all' or 'none'" % ', '.join(ALL_MODES))
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-handles', type=int, default=3,
+    ap.add_argument('--e2e-handles', type=int, default=4,
                     help='engine handles (one host thread each) used by the end-to-end loop; handles are per-thread objects like the htslib iterators they replace')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -416,11 +433,11 @@ def main():
         # gather consumes every read base once and writes every text byte once -> bytes_in + bytes_out; the entry pass reads the
         # staged reads once -> bytes_in (its entry strings are an intermediate, not algorithmic traffic)
         if write_ms >= size_ms:
-            dom, alg, dom_ms = 'k_mp_gather (entry strings -> text)', bytes_in + out_len, write_ms
+            dom, alg, dom_ms, dom_k = 'k_mp_gather (entry strings -> text)', bytes_in + out_len, write_ms, ['k_mp_gather']
         else:
-            dom, alg, dom_ms = 'k_mp_entries + k_ss_scan + k_ss_cols (reads -> entry strings, line sizes)', bytes_in, size_ms
+            dom, alg, dom_ms, dom_k = 'k_mp_entries + k_ss_scan + k_ss_cols (reads -> entry strings, line sizes)', bytes_in, size_ms, ['k_mp_entries', 'k_ss_scan', 'k_ss_cols']
         achieved = alg / (dom_ms * 1e-3) / 1e9
-        traffic = None                                   # measured under ncu only (profiles/), never in a timed run
+        traffic = measured_traffic(dom_k)                # from the round's ncu capture while the kernel sources are unchanged, else null
         value = world * ncols * args.steps / dt
         e2e = world * ncols * args.steps / dt_e2e
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

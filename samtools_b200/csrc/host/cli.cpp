@@ -99,20 +99,6 @@ struct Engine {
     }
 };
 
-// The engine addresses columns as 32-bit offsets from the window start.  Without
-// -a only positions under reads can be reported, so the window is shrunk to the
-// span of the batch (this is what lets 10^10-sized coordinates through).
-bool window_for(const PackedBatch &pb, int64_t beg, int64_t end, bool all, int64_t tid_len, int64_t &wbeg, int64_t &wend)
-{
-    wbeg = beg; wend = end;
-    if (!all && !pb.pos.empty()) {
-        int64_t lo = *std::min_element(pb.pos.begin(), pb.pos.end());
-        if (lo > wbeg) wbeg = lo;
-    }
-    const int64_t hi = all ? std::min(end, tid_len) : wbeg;
-    return hi - wbeg < (1LL << 31) - (1 << 20);
-}
-
 void write_all(FILE *fp, const std::vector<char> &buf, size_t n) { if (n) fwrite(buf.data(), 1, n, fp); }
 
 // ---- column windows ------------------------------------------------------------------------------------------------

@@ -20,3 +20,5 @@ fi
 make -s -C oracle
 g++ -std=c++17 -O2 -ffp-contract=off -Wno-unknown-pragmas -o tests/emul/_build/baq_host tests/emul/baq_host.cpp \
     -Loracle/_build -loracle -Wl,-rpath,"$PWD/oracle/_build" -lz -lm
+# the SIMD-within-a-register entry formatter of the device entry pass, exhaustively against the per-base definition
+g++ -std=c++17 -O2 -Wall -Wno-unused-function -Wno-parentheses -o tests/emul/_build/swar_check tests/emul/swar_check.cpp

@@ -71,3 +71,10 @@ def test_coverage_histogram_views(emul_bin, oracle_bin, corpus, tmp_path, monkey
     synth.write_sam(sam, soa)
     assert not hist_cases.run_all(emul_bin, oracle_bin, corpus, tmp_path, sam)
     assert not hist_cases.run_all(emul_bin, oracle_bin, corpus, tmp_path, sam, {'B200_WINDOW_COLS': '997'})
+
+
+def test_swar_entry_formatter_exhaustive(emul_bin):
+    """ent_group8_swar (plp_core.h: eight bases formatted SIMD-in-word by the device entry pass) == ent_plain for every
+    quality byte x base code x strand x -Q 0..127 x reference equal / different / absent, at every position of a group"""
+    r = subprocess.run([os.path.join(ROOT, 'tests', 'emul', '_build', 'swar_check')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and ' 0 mismatches' in r.stdout, r.stdout + r.stderr
