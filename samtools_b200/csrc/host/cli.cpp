@@ -25,6 +25,7 @@
 #include <cstring>
 #include <cerrno>
 #include <algorithm>
+#include <thread>
 #include <set>
 #include <unordered_map>
 
@@ -90,15 +91,30 @@ bool load_tid(FileData &fd, int tid, const char *cmd)
 struct Engine {
     b200_engine_t *e = nullptr;
     ~Engine() { if (e) b200_engine_destroy(e); }
-    bool init()
+    bool init(int dev = -1)
     {
-        int dev = 0;
-        if (const char *s = getenv("B200_DEVICE")) dev = atoi(s);
+        if (dev < 0) { dev = 0; if (const char *s = getenv("B200_DEVICE")) dev = atoi(s); }
         if (b200_engine_create(dev, &e) != 0) { fprintf(stderr, "b200samtools: cannot create the CUDA pileup engine (a B200/sm_100a device is required)\n"); return false; }
         return true;
     }
 };
-
+// Devices for the extra window workers of a driver: B200_DEVICES="0,1,2,3" (one handle each), times B200_HANDLES handles per
+// device (default 1).  The column windows of a reference sequence are independent (each stages its own halo), so they are
+// handed round-robin to the workers -- region sharding across GPUs below the Python layer, and, with several
+// handles on one device, H2D / kernels / D2H of consecutive windows overlapping.  Unset: one handle on B200_DEVICE.
+std::vector<int> worker_devices()
+{
+    std::vector<int> d;
+    if (const char *s = getenv("B200_DEVICES")) {
+        for (const char *p = s; *p;) { if (isdigit((unsigned char)*p)) { d.push_back(atoi(p)); while (isdigit((unsigned char)*p)) ++p; } else ++p; }
+    }
+    int per = 1;
+    if (const char *s = getenv("B200_HANDLES")) per = std::max(1, atoi(s));
+    if (d.empty() && per > 1) { int dev = 0; if (const char *s = getenv("B200_DEVICE")) dev = atoi(s); d.push_back(dev); }
+    std::vector<int> out;
+    for (int k = 0; k < per; ++k) for (int dev : d) out.push_back(dev);
+    return out;
+}
 void write_all(FILE *fp, const std::vector<char> &buf, size_t n) { if (n) fwrite(buf.data(), 1, n, fp); }
 
 // ---- column windows ------------------------------------------------------------------------------------------------
@@ -237,6 +253,13 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
     std::vector<char> out;
     std::vector<int64_t> bb, be;
     const int nref = h.n_ref();
+    // extra window workers (worker_devices()): each has its own engine handle, packer, cursors and output buffer
+    struct Worker { Engine eng; PackedBatch pb; std::vector<char> out; std::vector<size_t> sel, cursor; size_t need = 0; int rc = 0; std::string err; };
+    std::vector<std::unique_ptr<Worker>> workers;
+    if (!o.gl && o.xcols.empty()) {
+        const std::vector<int> wd = worker_devices();
+        if (wd.size() > 1) for (int dev : wd) { workers.emplace_back(new Worker()); if (!workers.back()->eng.init(dev)) return 1; workers.back()->cursor.assign((size_t)nfn, 0); }
+    }
     std::vector<size_t> sel; std::vector<size_t> cursor((size_t)nfn);
     std::vector<std::vector<uint8_t>> hbits((size_t)nfn);   // host bits of the contig's records, decided ONCE (the BQ:Z path edits the record)
     std::vector<const Record *> staged;                     // records of the staged window, batch order (host columns)
@@ -336,6 +359,46 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
                 if (st.n_kept_in_window > 0) { first_hit = wb; break; }
             }
             if (first_hit < 0) return 0;
+        }
+        if (with_reads && !workers.empty()) {
+            // rounds of one window per worker, run concurrently, written in window order
+            std::vector<std::pair<int64_t, int64_t>> wins;
+            for (int64_t wb = lo_col; wb < hi_col; wb += W) wins.emplace_back(wb, std::min(wb + W, hi_col));
+            for (auto &w : workers) std::fill(w->cursor.begin(), w->cursor.end(), 0);
+            const size_t K = workers.size();
+            for (size_t base = 0; base < wins.size(); base += K) {
+                const size_t m = std::min(K, wins.size() - base);
+                std::vector<std::thread> th;
+                for (size_t t = 0; t < m; ++t) th.emplace_back([&, t]() {
+                    Worker &w = *workers[t];
+                    const int64_t wb = wins[base + t].first, we = wins[base + t].second;
+                    w.rc = 0; w.need = 0;
+                    w.pb.clear();
+                    for (int i = 0; i < nfn; ++i) {
+                        w.pb.begin_file();
+                        if (tid < (int)fd[(size_t)i].by_tid.size()) {
+                            std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
+                            window_records(v, w.cursor[(size_t)i], wb, we, w.sel);
+                            for (size_t j : w.sel) w.pb.add(v[j], hbits[(size_t)i][j], o.overlaps);
+                        }
+                    }
+                    w.pb.finish();
+                    b200_batch_t batch = w.pb.view(tid, h.lens[(size_t)tid], name, ref);
+                    b200_stage_conf_t wsc = sc; wsc.beg = wb; wsc.end = we;
+                    b200_stage_stats_t st;
+                    if (b200_stage(w.eng.e, &batch, &wsc, &st) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); return; }
+                    if (!o.all && st.n_kept_in_window == 0) return;
+                    const size_t bound = (size_t)b200_mpileup_text_bound(w.eng.e, &mc);
+                    if (w.out.size() < bound + 64) w.out.resize(bound + 64);
+                    if (b200_mpileup_text(w.eng.e, &mc, w.out.data(), w.out.size(), &w.need) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); }
+                });
+                for (auto &t : th) t.join();
+                for (size_t t = 0; t < m; ++t) {
+                    if (workers[t]->rc != 0) { fprintf(stderr, "samtools mpileup: %s\n", workers[t]->err.c_str()); return -1; }
+                    write_all(fp, workers[t]->out, workers[t]->need);
+                }
+            }
+            return 1;
         }
         std::fill(cursor.begin(), cursor.end(), 0);
         for (int64_t wb = lo_col; wb < hi_col || (!with_reads && wb == lo_col); wb += W) {
@@ -595,6 +658,13 @@ int main_depth(int argc, char **argv)
         }
     };
     std::vector<size_t> sel; std::vector<size_t> cursor((size_t)nfn);
+    // extra window workers (worker_devices()): one engine handle, packer, cursors and output buffer each
+    struct Worker { Engine eng; PackedBatch pb; std::vector<char> out; std::vector<size_t> sel, cursor; size_t need = 0; int rc = 0; std::string err; };
+    std::vector<std::unique_ptr<Worker>> workers;
+    {
+        const std::vector<int> wd = worker_devices();
+        if (wd.size() > 1) for (int dev : wd) { workers.emplace_back(new Worker()); if (!workers.back()->eng.init(dev)) return 1; workers.back()->cursor.assign((size_t)nfn, 0); }
+    }
     auto stage_window = [&](int tid, bool with_reads, int64_t wb, int64_t we, b200_stage_stats_t &st) -> int {
         pb.clear();
         for (int i = 0; i < nfn; ++i) {
@@ -633,6 +703,48 @@ int main_depth(int argc, char **argv)
                 seen = st.n_kept > 0;
             }
             if (!seen) return 0;
+        }
+        if (with_reads && !workers.empty()) {
+            // rounds of one window per worker, run concurrently, written in window order (see the mpileup driver)
+            std::vector<std::pair<int64_t, int64_t>> wins;
+            for (int64_t wb = lo_col; wb < hi_col; wb += W) wins.emplace_back(wb, std::min(wb + W, hi_col));
+            for (auto &w : workers) std::fill(w->cursor.begin(), w->cursor.end(), 0);
+            const size_t K = workers.size();
+            for (size_t base = 0; base < wins.size(); base += K) {
+                const size_t m = std::min(K, wins.size() - base);
+                std::vector<std::thread> th;
+                for (size_t t = 0; t < m; ++t) th.emplace_back([&, t]() {
+                    Worker &w = *workers[t];
+                    const int64_t wb = wins[base + t].first, we = wins[base + t].second;
+                    w.rc = 0; w.need = 0;
+                    w.pb.clear();
+                    for (int i = 0; i < nfn; ++i) {
+                        w.pb.begin_file();
+                        if (tid < (int)fd[(size_t)i].by_tid.size()) {
+                            std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
+                            window_records(v, w.cursor[(size_t)i], wb, we, w.sel);
+                            for (size_t j : w.sel) {
+                                w.pb.add(v[j], 0, false);
+                                if (remove_overlaps) w.pb.depth_clip.push_back(clips[(size_t)i][(size_t)tid][j]);
+                            }
+                        }
+                    }
+                    w.pb.finish();
+                    b200_batch_t batch = w.pb.view(tid, h.lens[(size_t)tid], h.names[(size_t)tid], nullptr);
+                    b200_stage_conf_t wsc = sc; wsc.beg = wb; wsc.end = we;
+                    b200_stage_stats_t st;
+                    if (b200_stage(w.eng.e, &batch, &wsc, &st) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); return; }
+                    const size_t bound = (size_t)b200_depth_text_bound(w.eng.e);
+                    if (w.out.size() < bound + 64) w.out.resize(bound + 64);
+                    if (b200_depth_text(w.eng.e, &dc, w.out.data(), w.out.size(), &w.need) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); }
+                });
+                for (auto &t : th) t.join();
+                for (size_t t = 0; t < m; ++t) {
+                    if (workers[t]->rc != 0) { fprintf(stderr, "samtools depth: %s\n", workers[t]->err.c_str()); return -1; }
+                    write_all(fp, workers[t]->out, workers[t]->need);
+                }
+            }
+            return 1;
         }
         std::fill(cursor.begin(), cursor.end(), 0);
         for (int64_t wb = lo_col; wb < hi_col || (!with_reads && wb == lo_col); wb += W) {

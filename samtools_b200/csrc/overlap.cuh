@@ -27,11 +27,25 @@ __global__ void k_overlap(RawSoA r, const int64_t *next, const uint8_t *state, c
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < r.n) overlap_chain(r, i, next, state, rlen, file_start, n_files, pairs, n_pairs);
 }
-// the quality tweak of every collected pair, one thread per pair (the count stays on the device: no host round trip)
-__global__ void k_overlap_tweak(RawSoA r, const int32_t *pairs, const unsigned int *n_pairs)
+// the quality tweak of every collected pair (the count stays on the device: no host round trip).  One WARP per pair: two
+// mates of the simple shape share a span in which every position is independent (plp_stage.h overlap_span_simple), so the
+// lanes take every 32nd position; any other pair is walked in lock-step by lane 0 (tweak_overlap).
+__global__ void __launch_bounds__(128) k_overlap_tweak(RawSoA r, const ReadDesc *desc, const int32_t *rlen, const int32_t *pairs, const unsigned int *n_pairs)
 {
     const unsigned int n = *n_pairs;
-    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) tweak_overlap(r, pairs[2 * (size_t)k], pairs[2 * (size_t)k + 1]);
+    const int lane = threadIdx.x & 31;
+    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int k = warp; k < n; k += n_warps) {
+        const int64_t ia = pairs[2 * (size_t)k], ib = pairs[2 * (size_t)k + 1];
+        const ReadDesc da = load_hot(desc + ia), db = load_hot(desc + ib);
+        if ((da.fl & RD_SIMPLE) && (db.fl & RD_SIMPLE)) {
+            const OvSpan sp = overlap_span_simple(r, da, db, rlen, ia, ib);
+            uint8_t *aq = r.qual + r.qual_off[ia], *bq = r.qual + r.qual_off[ib];
+            const uint64_t aoff = r.qual_off[ia], boff = r.qual_off[ib];
+            const int amul = (r.rbits && (r.rbits[ia] & B200_RB_NAME_ODD)) ? 1 : 0;
+            for (int32_t j = lane; j < sp.n; j += 32) tweak_pos(r.seq4, aq, bq, aoff, boff, sp.a0 + j, sp.b0 + j, amul);
+        } else if (lane == 0) tweak_overlap(r, ia, ib);
+    }
 }
 __global__ void k_depth_clip(RawSoA r, const int64_t *next, const uint8_t *state, const int32_t *rlen, int32_t *clip, int64_t win_base)
 {
@@ -57,8 +71,8 @@ int launch_overlap(b200_engine *e, const RawSoA &r)
     if (ensure(e, e->ov_pairs, e->cap_ov_pairs, (size_t)r.n + 2)) return -1;      // at most n/2 pairs of two indices
     CK(cudaMemsetAsync(e->d_misc + 40, 0, 8, e->stream));
     k_overlap<<<nblk(r.n, 128), 128, 0, e->stream>>>(r, e->next, e->state, e->rlen, e->file_start, e->n_files, e->ov_pairs, (unsigned int *)(e->d_misc + 40)); e->launches++;
-    const int gt = (int)std::min<int64_t>(nblk(r.n / 2 + 1, 128), (int64_t)e->n_sm * 16);
-    k_overlap_tweak<<<gt, 128, 0, e->stream>>>(r, e->ov_pairs, (const unsigned int *)(e->d_misc + 40)); e->launches++;
+    const int gt = (int)std::min<int64_t>(nblk((r.n / 2 + 1) * 32, 128), (int64_t)e->n_sm * 16);
+    k_overlap_tweak<<<gt, 128, 0, e->stream>>>(r, e->desc, e->rlen, e->ov_pairs, (const unsigned int *)(e->d_misc + 40)); e->launches++;
     CK(cudaGetLastError());
     return 0;
 }

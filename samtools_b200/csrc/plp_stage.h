@@ -267,6 +267,21 @@ PLP_HD int cw_next(CWalk &w)
     return -1;
 }
 
+// the rule for one reference position where both mates have a base (htslib tweak_overlap_quality): equal bases pool their
+// qualities (capped at 200) onto the mate the name hash picks, the other gets 0; different bases: the better one keeps
+// 0.8 of its quality, the other gets 0
+PLP_HD void tweak_pos(const uint8_t *seq4, uint8_t *aq, uint8_t *bq, uint64_t aoff, uint64_t boff, int32_t ja, int32_t jb, int amul)
+{
+    const int bmul = 1 - amul;
+    const int qa = aq[ja], qb = bq[jb];
+    if (base4(seq4, aoff, ja) == base4(seq4, boff, jb)) {
+        int q = qa + qb; if (q > 200) q = 200;
+        aq[ja] = (uint8_t)(amul * q); bq[jb] = (uint8_t)(bmul * q);
+    } else if (qa > qb) { aq[ja] = (uint8_t)(0.8 * qa); bq[jb] = 0; }
+    else if (qa < qb) { bq[jb] = (uint8_t)(0.8 * qb); aq[ja] = 0; }
+    else { aq[ja] = (uint8_t)(amul * 0.8 * qa); bq[jb] = (uint8_t)(bmul * 0.8 * qb); }
+}
+
 // a = mate buffered first, b = mate arriving now
 PLP_HD void tweak_overlap(const RawSoA &r, int64_t ia, int64_t ib)
 {
@@ -308,14 +323,24 @@ PLP_HD void tweak_overlap(const RawSoA &r, int64_t ia, int64_t ib)
             } else continue;
         }
         if (A.iseq > alq || B.iseq > blq) return;
-        const int qa = aq[A.iseq], qb = bq[B.iseq];
-        if (base4(r.seq4, aoff, (int32_t)A.iseq) == base4(r.seq4, boff, (int32_t)B.iseq)) {
-            int q = qa + qb; if (q > 200) q = 200;
-            aq[A.iseq] = (uint8_t)(amul * q); bq[B.iseq] = (uint8_t)(bmul * q);
-        } else if (qa > qb) { aq[A.iseq] = (uint8_t)(0.8 * qa); bq[B.iseq] = 0; }
-        else if (qa < qb) { bq[B.iseq] = (uint8_t)(0.8 * qb); aq[A.iseq] = 0; }
-        else { aq[A.iseq] = (uint8_t)(amul * 0.8 * qa); bq[B.iseq] = (uint8_t)(bmul * 0.8 * qb); }
+        tweak_pos(r.seq4, aq, bq, aoff, boff, (int32_t)A.iseq, (int32_t)B.iseq, amul);
     }
+}
+
+// Both mates of the shape [H][S]<n>M[S][H] (RD_SIMPLE): over the shared reference span [bpos, min(aend, bend)) every position
+// has a base in both reads and the rule above is applied position by position, independently -- position k of the span is
+// query base a0 + k of the first mate and b0 + k of the second (what the lock-step CIGAR walk of tweak_overlap visits, in
+// the same order).  The device gives a warp to a pair and a lane to every 32nd position.
+struct OvSpan { int32_t a0, b0, n; };
+PLP_HD OvSpan overlap_span_simple(const RawSoA &r, const ReadDesc &da, const ReadDesc &db, const int32_t *rlen, int64_t ia, int64_t ib)
+{
+    OvSpan s;
+    const int64_t apos = r.pos[ia], bpos = r.pos[ib];
+    const int64_t aend = apos + rlen[ia], bend = bpos + rlen[ib];
+    const int64_t e = aend < bend ? aend : bend;
+    s.a0 = (int32_t)da.qstart + (int32_t)(bpos - apos); s.b0 = (int32_t)db.qstart;
+    s.n = (bpos >= apos && e > bpos) ? (int32_t)(e - bpos) : 0;
+    return s;
 }
 
 // one thread per name chain: replay overlap_push / overlap_remove.  pairs == nullptr: the quality tweak of a pair runs
@@ -323,7 +348,8 @@ PLP_HD void tweak_overlap(const RawSoA &r, int64_t ia, int64_t ib)
 // kernel with one thread per PAIR -- a read takes part in at most one tweak, so the pairs are independent, and a warp
 // of tweaks keeps all its lanes busy where a warp of chains has ~15 % of them walking CIGARs.
 PLP_HD void overlap_chain(const RawSoA &r, int64_t i, const int64_t *next, const uint8_t *state, const int32_t *rlen,
-                          const int64_t *file_start, int n_files, int32_t *pairs = nullptr, unsigned int *n_pairs = nullptr)
+                          const int64_t *file_start, int n_files, int32_t *pairs = nullptr, unsigned int *n_pairs = nullptr,
+                          const ReadDesc *desc = nullptr, int *xcheck_bad = nullptr)
 {
     if (r.prev[i] >= 0 || next[i] < 0) return;   // not the head of a chain of >= 2
     int f = 0;
@@ -355,7 +381,34 @@ PLP_HD void overlap_chain(const RawSoA &r, int64_t i, const int64_t *next, const
                 const unsigned int k = atomicAdd(n_pairs, 1u);
                 pairs[2 * (size_t)k] = (int32_t)stored; pairs[2 * (size_t)k + 1] = (int32_t)x;
 #endif
-            } else tweak_overlap(r, stored, x);
+            } else {
+#if !defined(__CUDA_ARCH__)
+                // emulation harness: the per-position fast path the device uses for two simple mates must rewrite the
+                // qualities exactly like the lock-step walk
+                if (desc && xcheck_bad && (desc[stored].fl & RD_SIMPLE) && (desc[x].fl & RD_SIMPLE)) {
+                    const int la = r.l_qseq[stored], lb = r.l_qseq[x];
+                    uint8_t *aq = r.qual + r.qual_off[stored], *bq = r.qual + r.qual_off[x];
+                    uint8_t ca[1024], cb[1024];
+                    if (la <= 1024 && lb <= 1024) {
+                        for (int k = 0; k < la; ++k) ca[k] = aq[k];
+                        for (int k = 0; k < lb; ++k) cb[k] = bq[k];
+                        const OvSpan sp = overlap_span_simple(r, desc[stored], desc[x], rlen, stored, x);
+                        const int amul = (r.rbits && (r.rbits[stored] & B200_RB_NAME_ODD)) ? 1 : 0;
+                        // on copies laid out like the originals: tweak_pos addresses bases through the nibble offsets
+                        for (int k = 0; k < sp.n; ++k) {
+                            uint8_t *pa = ca - 0, *pb = cb - 0;
+                            tweak_pos(r.seq4, pa, pb, r.qual_off[stored], r.qual_off[x], sp.a0 + k, sp.b0 + k, amul);
+                        }
+                        tweak_overlap(r, stored, x);
+                        for (int k = 0; k < la; ++k) if (ca[k] != aq[k]) ++*xcheck_bad;
+                        for (int k = 0; k < lb; ++k) if (cb[k] != bq[k]) ++*xcheck_bad;
+                        stored = -1;
+                        continue;
+                    }
+                }
+#endif
+                tweak_overlap(r, stored, x);
+            }
             stored = -1;
         }
     }

@@ -176,7 +176,9 @@ int b200_stage(b200_engine_t *e, const b200_batch_t *b, const b200_stage_conf_t 
         e->next.assign((size_t)n + 1, -1);
         for (int64_t i = 0; i < n; ++i) if (b->prev_same_name[i] >= 0) e->next[(size_t)b->prev_same_name[i]] = i;
         if (cf->mode == B200_MODE_MPILEUP) {
-            for (int64_t i = 0; i < n; ++i) overlap_chain(r, i, e->next.data(), e->state.data(), e->rlen.data(), b->file_start, b->n_files);
+            int bad = 0;   // cross-check of the device's simple-pair fast path (plp_stage.h overlap_span_simple / tweak_pos)
+            for (int64_t i = 0; i < n; ++i) overlap_chain(r, i, e->next.data(), e->state.data(), e->rlen.data(), b->file_start, b->n_files, nullptr, nullptr, e->desc.data(), &bad);
+            if (bad) { e->err = "emulation harness: per-position overlap tweak differs from the lock-step walk"; return -1; }
         } else {
             e->clip.assign((size_t)n + 1, INT32_MIN);
             for (int64_t i = 0; i < n; ++i) depth_clip_chain(r, i, e->next.data(), e->state.data(), e->rlen.data(), e->clip.data(), e->win_base);

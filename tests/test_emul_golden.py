@@ -73,8 +73,29 @@ def test_coverage_histogram_views(emul_bin, oracle_bin, corpus, tmp_path, monkey
     assert not hist_cases.run_all(emul_bin, oracle_bin, corpus, tmp_path, sam, {'B200_WINDOW_COLS': '997'})
 
 
-def test_swar_entry_formatter_exhaustive(emul_bin):
+def test_swar_entry_formatter_exhaustive(tmp_path):
     """ent_group8_swar (plp_core.h: eight bases formatted SIMD-in-word by the device entry pass) == ent_plain for every
     quality byte x base code x strand x -Q 0..127 x reference equal / different / absent, at every position of a group"""
-    r = subprocess.run([os.path.join(ROOT, 'tests', 'emul', '_build', 'swar_check')], capture_output=True, text=True, timeout=600)
+    exe = str(tmp_path / 'swar_check')      # built here: pytest-xdist workers rebuild tests/emul/_build concurrently
+    subprocess.run(['g++', '-std=c++17', '-O2', '-Wno-parentheses', '-o', exe, os.path.join(ROOT, 'tests', 'emul', 'swar_check.cpp')], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and ' 0 mismatches' in r.stdout, r.stdout + r.stderr
+
+
+def test_window_workers(emul_bin, oracle_bin, corpus, monkeypatch):
+    """B200_DEVICES / B200_HANDLES: the mpileup driver hands the column windows of a reference sequence round-robin to several
+    engine handles (one per listed device; threads) and writes their text in window order.  Every golden mpileup / depth case with
+    97-column windows over three workers must still reproduce the reference's bytes."""
+    from concurrent.futures import ThreadPoolExecutor
+    monkeypatch.setenv('B200_WINDOW_COLS', '97')
+    monkeypatch.setenv('B200_DEVICES', '0,0,0')
+    todo = [c for c in CASES if not c['skip'] and '>' not in c['cmd'] and ('mpileup' in c['cmd'] or 'depth' in c['cmd'])]
+
+    def run(c):
+        ok, out, err = golden_cases.run_case(c, emul_bin, oracle_bin, corpus)
+        if not ok and (b'BAQ kernel is not emulated' in err or b'not available on the device path' in err):
+            return None
+        return None if ok else (c['id'], c['cmd'], err[-200:])
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        bad = [r for r in ex.map(run, todo) if r]
+    assert len(todo) > 100 and not bad, bad[:3]

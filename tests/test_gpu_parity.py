@@ -404,3 +404,24 @@ def test_coverage_histogram_views_on_gpu(cli, oracle_bin, corpus, tmp_path):
     synth.write_sam(sam, soa)
     assert not hist_cases.run_all(cli, oracle_bin, corpus, tmp_path, sam)
     assert not hist_cases.run_all(cli, oracle_bin, corpus, tmp_path, sam, {'B200_WINDOW_COLS': '997'})
+
+
+# ---------------------------------------------------------------- several engine handles behind one driver (B200_DEVICES / B200_HANDLES)
+def test_window_workers_on_gpu(cli, oracle_bin, corpus, monkeypatch):
+    """the drivers hand column windows round-robin to several handles (threads; one per listed device -- here the same device
+    three times, plus every other visible device) and write the text in window order: mpileup (BAQ, overlaps) and depth goldens"""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    devs = ['0', '0', '0'] + [str(d) for d in range(1, torch.cuda.device_count())]
+    monkeypatch.setenv('B200_WINDOW_COLS', '97')
+    monkeypatch.setenv('B200_DEVICES', ','.join(devs))
+    todo = [c for c in CASES if not c['skip'] and '>' not in c['cmd'] and ('mpileup' in c['cmd'] or 'depth' in c['cmd'])][::3]
+
+    def run(c):
+        ok, out, err = golden_cases.run_case(c, cli, oracle_bin, corpus)
+        if not ok and b'not available on the device path' in err:
+            return None
+        return None if ok else (c['id'], c['cmd'], err[-200:])
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        bad = [r for r in ex.map(run, todo) if r]
+    assert len(todo) > 30 and not bad, bad[:3]
