@@ -5,6 +5,13 @@ set -e
 # while others execute the binaries ("text file busy" otherwise)
 cd "$(dirname "$0")/../.."
 mkdir -p tests/emul/_build
+# up to date?  (every output present and no source newer than the oldest of them: four test modules call this script)
+stamp=tests/emul/_build/.stamp
+if [ -f "$stamp" ] && [ -f tests/emul/_build/b200samtools_emul ] && [ -f tests/emul/_build/plp_dump_emul ] && [ -f tests/emul/_build/baq_host ] && \
+   [ -z "$(find samtools_b200/csrc include tests/emul tests/compat oracle -maxdepth 2 -type f \( -name '*.cpp' -o -name '*.h' -o -name '*.hpp' -o -name '*.cuh' -o -name '*.c' -o -name '*.sh' -o -name Makefile \) -newer "$stamp" 2>/dev/null | head -1)" ]; then
+    exit 0
+fi
+touch tests/emul/_build/.stamp.new
 g++ -std=c++17 -O1 -g -ffp-contract=off -Wall -Wno-unused-function -o tests/emul/_build/b200samtools_emul.tmp$$ \
     samtools_b200/csrc/host/cli.cpp samtools_b200/csrc/host/hts_io.cpp tests/emul/emul_engine.cpp -lz
 # the htslib-compatible iterator tier (plp_compat.cpp) + its test client, on the emulation harness
@@ -24,3 +31,4 @@ g++ -std=c++17 -O2 -ffp-contract=off -Wno-unknown-pragmas -o tests/emul/_build/b
     -Loracle/_build -loracle -Wl,-rpath,"$PWD/oracle/_build" -lz -lm
 
 for f in b200samtools_emul baq_host plbuf_dump_emul plp_dump_emul ref_bam_plbuf.o; do if [ -f tests/emul/_build/$f.tmp$$ ]; then mv -f tests/emul/_build/$f.tmp$$ tests/emul/_build/$f; fi; done
+mv -f tests/emul/_build/.stamp.new tests/emul/_build/.stamp
