@@ -97,6 +97,38 @@ def usable_cores():
     return n, {'os_cpu_count': os.cpu_count(), 'sched_affinity': aff, 'cgroup_quota_cpus': quota}
 
 
+def bind_to_gpu_numa(local):
+    """Keep this rank's host threads -- and, by first touch, the pinned buffers they allocate -- on the NUMA node its GPU hangs
+    off (8 ranks x 4 handles share two root complexes otherwise: the e2e leg of the 1->8 curve is PCIe/host-memory bound).
+    Best effort: any missing piece (NVML, sysfs NUMA info, a cpuset that excludes the node) leaves the affinity untouched."""
+    info = {'bound': False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(vis.split(',')[local]) if vis and vis.split(',')[local].strip().isdigit() else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(':', 1)
+        dev = os.path.join('/sys/bus/pci/devices', (dom[-4:] + ':' + rest).lower())
+        node = int(open(os.path.join(dev, 'numa_node')).read())
+        info['node'] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        target = os.sched_getaffinity(0) & cpus
+        info['cpus'] = len(target)
+        if len(target) >= 8:
+            os.sched_setaffinity(0, target)
+            info['bound'] = True
+    except Exception as e:                                      # noqa: BLE001 -- measurement aid only
+        info['note'] = str(e)[:100]
+    return info
+
+
 class ClockSampler:
     """SM clock + throttle reasons of one GPU, polled through NVML every few ms while the timed
     regions run (the recipe's nvidia-smi query, without the process start-up latency)."""
@@ -310,6 +342,7 @@ def main():
 
     rank = int(os.environ.get('RANK', '0')); world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    numa = bind_to_gpu_numa(local) if world > 1 else {'bound': False, 'note': 'single rank: not bound'}
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device (the pileup engine has no CPU fallback)')
     torch.cuda.set_device(local)
@@ -452,7 +485,7 @@ def main():
                              'step_kernels_ms': {'read_stage': float(np.mean(stage_ms)), 'entry_pass': size_ms, 'tile_offset_scan': scan_ms,
                                                  'gather': write_ms, 'column_stage_total': kms, 'total': kms + float(np.mean(stage_ms))},
                              'step_frac': (bytes_in + out_len) / ((kms + float(np.mean(stage_ms))) * 1e-3) / 1e9 / peak},
-                'reads_per_step_per_gpu': n_reads}
+                'reads_per_step_per_gpu': n_reads, 'numa': numa}
 
     # ------------------------------------------------------------------------------------ further BASELINE configurations
     sub = {}
