@@ -416,7 +416,7 @@ int bam_plp_insertion(const bam_pileup1_t *p, kstring_t *ins, int *del_len)
     }
     b200_plp_insertion(p, ins->s, (int)ins->m, &dl);
     ins->s[n] = 0; ins->l = (size_t)n;
-    if (del_len) *del_len = dl;
+    if (del_len && p->indel > 0) *del_len = dl;          // htslib leaves *del_len untouched when the column has no insertion
     return n;
 }
 
