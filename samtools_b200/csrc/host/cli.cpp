@@ -117,6 +117,35 @@ std::vector<int> worker_devices()
 }
 void write_all(FILE *fp, const std::vector<char> &buf, size_t n) { if (n) fwrite(buf.data(), 1, n, fp); }
 
+// One extra window worker of a driver: its own engine handle, packer, record cursors and output buffer.
+struct WinWorker { Engine eng; PackedBatch pb; std::vector<char> out; std::vector<size_t> sel, cursor; size_t need = 0; int rc = 0; std::string err; };
+bool make_workers(std::vector<std::unique_ptr<WinWorker>> &workers, int n_files)
+{
+    const std::vector<int> wd = worker_devices();
+    if (wd.size() < 2) return true;
+    for (int dev : wd) { workers.emplace_back(new WinWorker()); if (!workers.back()->eng.init(dev)) return false; workers.back()->cursor.assign((size_t)n_files, 0); }
+    return true;
+}
+// Rounds of one window per worker: job(worker, wb, we) packs, stages and formats its window concurrently with the others
+// (setting rc / err / need), then the texts are written in window order.
+template <class Job>
+int run_window_rounds(std::vector<std::unique_ptr<WinWorker>> &workers, const std::vector<std::pair<int64_t, int64_t>> &wins, FILE *fp, const char *tool, Job job)
+{
+    for (auto &w : workers) std::fill(w->cursor.begin(), w->cursor.end(), 0);
+    const size_t K = workers.size();
+    for (size_t base = 0; base < wins.size(); base += K) {
+        const size_t m = std::min(K, wins.size() - base);
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < m; ++t) th.emplace_back([&, t]() { WinWorker &w = *workers[t]; w.rc = 0; w.need = 0; job(w, wins[base + t].first, wins[base + t].second); });
+        for (auto &t : th) t.join();
+        for (size_t t = 0; t < m; ++t) {
+            if (workers[t]->rc != 0) { fprintf(stderr, "samtools %s: %s\n", tool, workers[t]->err.c_str()); return -1; }
+            write_all(fp, workers[t]->out, workers[t]->need);
+        }
+    }
+    return 0;
+}
+
 // ---- column windows ------------------------------------------------------------------------------------------------
 // The engine addresses columns as 32-bit offsets from the window start and takes < 4 GiB of read payload per staged
 // batch, so the drivers cut a reference sequence into windows of at most window_cols() columns.  A window [wb,we)
@@ -253,13 +282,9 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
     std::vector<char> out;
     std::vector<int64_t> bb, be;
     const int nref = h.n_ref();
-    // extra window workers (worker_devices()): each has its own engine handle, packer, cursors and output buffer
-    struct Worker { Engine eng; PackedBatch pb; std::vector<char> out; std::vector<size_t> sel, cursor; size_t need = 0; int rc = 0; std::string err; };
-    std::vector<std::unique_ptr<Worker>> workers;
-    if (!o.gl && o.xcols.empty()) {
-        const std::vector<int> wd = worker_devices();
-        if (wd.size() > 1) for (int dev : wd) { workers.emplace_back(new Worker()); if (!workers.back()->eng.init(dev)) return 1; workers.back()->cursor.assign((size_t)nfn, 0); }
-    }
+    // extra window workers (worker_devices()): the text path without host columns can be spread over several handles
+    std::vector<std::unique_ptr<WinWorker>> workers;
+    if (!o.gl && o.xcols.empty() && !make_workers(workers, nfn)) return 1;
     std::vector<size_t> sel; std::vector<size_t> cursor((size_t)nfn);
     std::vector<std::vector<uint8_t>> hbits((size_t)nfn);   // host bits of the contig's records, decided ONCE (the BQ:Z path edits the record)
     std::vector<const Record *> staged;                     // records of the staged window, batch order (host columns)
@@ -361,43 +386,29 @@ int run_mpileup(MpOpts &o, const std::vector<std::string> &fn)
             if (first_hit < 0) return 0;
         }
         if (with_reads && !workers.empty()) {
-            // rounds of one window per worker, run concurrently, written in window order
             std::vector<std::pair<int64_t, int64_t>> wins;
             for (int64_t wb = lo_col; wb < hi_col; wb += W) wins.emplace_back(wb, std::min(wb + W, hi_col));
-            for (auto &w : workers) std::fill(w->cursor.begin(), w->cursor.end(), 0);
-            const size_t K = workers.size();
-            for (size_t base = 0; base < wins.size(); base += K) {
-                const size_t m = std::min(K, wins.size() - base);
-                std::vector<std::thread> th;
-                for (size_t t = 0; t < m; ++t) th.emplace_back([&, t]() {
-                    Worker &w = *workers[t];
-                    const int64_t wb = wins[base + t].first, we = wins[base + t].second;
-                    w.rc = 0; w.need = 0;
-                    w.pb.clear();
-                    for (int i = 0; i < nfn; ++i) {
-                        w.pb.begin_file();
-                        if (tid < (int)fd[(size_t)i].by_tid.size()) {
-                            std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
-                            window_records(v, w.cursor[(size_t)i], wb, we, w.sel);
-                            for (size_t j : w.sel) w.pb.add(v[j], hbits[(size_t)i][j], o.overlaps);
-                        }
+            const int rc = run_window_rounds(workers, wins, fp, "mpileup", [&](WinWorker &w, int64_t wb, int64_t we) {
+                w.pb.clear();
+                for (int i = 0; i < nfn; ++i) {
+                    w.pb.begin_file();
+                    if (tid < (int)fd[(size_t)i].by_tid.size()) {
+                        std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
+                        window_records(v, w.cursor[(size_t)i], wb, we, w.sel);
+                        for (size_t j : w.sel) w.pb.add(v[j], hbits[(size_t)i][j], o.overlaps);
                     }
-                    w.pb.finish();
-                    b200_batch_t batch = w.pb.view(tid, h.lens[(size_t)tid], name, ref);
-                    b200_stage_conf_t wsc = sc; wsc.beg = wb; wsc.end = we;
-                    b200_stage_stats_t st;
-                    if (b200_stage(w.eng.e, &batch, &wsc, &st) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); return; }
-                    if (!o.all && st.n_kept_in_window == 0) return;
-                    const size_t bound = (size_t)b200_mpileup_text_bound(w.eng.e, &mc);
-                    if (w.out.size() < bound + 64) w.out.resize(bound + 64);
-                    if (b200_mpileup_text(w.eng.e, &mc, w.out.data(), w.out.size(), &w.need) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); }
-                });
-                for (auto &t : th) t.join();
-                for (size_t t = 0; t < m; ++t) {
-                    if (workers[t]->rc != 0) { fprintf(stderr, "samtools mpileup: %s\n", workers[t]->err.c_str()); return -1; }
-                    write_all(fp, workers[t]->out, workers[t]->need);
                 }
-            }
+                w.pb.finish();
+                b200_batch_t batch = w.pb.view(tid, h.lens[(size_t)tid], name, ref);
+                b200_stage_conf_t wsc = sc; wsc.beg = wb; wsc.end = we;
+                b200_stage_stats_t st;
+                if (b200_stage(w.eng.e, &batch, &wsc, &st) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); return; }
+                if (!o.all && st.n_kept_in_window == 0) return;
+                const size_t bound = (size_t)b200_mpileup_text_bound(w.eng.e, &mc);
+                if (w.out.size() < bound + 64) w.out.resize(bound + 64);
+                if (b200_mpileup_text(w.eng.e, &mc, w.out.data(), w.out.size(), &w.need) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); }
+            });
+            if (rc != 0) return -1;
             return 1;
         }
         std::fill(cursor.begin(), cursor.end(), 0);
@@ -658,13 +669,8 @@ int main_depth(int argc, char **argv)
         }
     };
     std::vector<size_t> sel; std::vector<size_t> cursor((size_t)nfn);
-    // extra window workers (worker_devices()): one engine handle, packer, cursors and output buffer each
-    struct Worker { Engine eng; PackedBatch pb; std::vector<char> out; std::vector<size_t> sel, cursor; size_t need = 0; int rc = 0; std::string err; };
-    std::vector<std::unique_ptr<Worker>> workers;
-    {
-        const std::vector<int> wd = worker_devices();
-        if (wd.size() > 1) for (int dev : wd) { workers.emplace_back(new Worker()); if (!workers.back()->eng.init(dev)) return 1; workers.back()->cursor.assign((size_t)nfn, 0); }
-    }
+    std::vector<std::unique_ptr<WinWorker>> workers;      // extra window workers (worker_devices())
+    if (!make_workers(workers, nfn)) return 1;
     auto stage_window = [&](int tid, bool with_reads, int64_t wb, int64_t we, b200_stage_stats_t &st) -> int {
         pb.clear();
         for (int i = 0; i < nfn; ++i) {
@@ -705,45 +711,31 @@ int main_depth(int argc, char **argv)
             if (!seen) return 0;
         }
         if (with_reads && !workers.empty()) {
-            // rounds of one window per worker, run concurrently, written in window order (see the mpileup driver)
             std::vector<std::pair<int64_t, int64_t>> wins;
             for (int64_t wb = lo_col; wb < hi_col; wb += W) wins.emplace_back(wb, std::min(wb + W, hi_col));
-            for (auto &w : workers) std::fill(w->cursor.begin(), w->cursor.end(), 0);
-            const size_t K = workers.size();
-            for (size_t base = 0; base < wins.size(); base += K) {
-                const size_t m = std::min(K, wins.size() - base);
-                std::vector<std::thread> th;
-                for (size_t t = 0; t < m; ++t) th.emplace_back([&, t]() {
-                    Worker &w = *workers[t];
-                    const int64_t wb = wins[base + t].first, we = wins[base + t].second;
-                    w.rc = 0; w.need = 0;
-                    w.pb.clear();
-                    for (int i = 0; i < nfn; ++i) {
-                        w.pb.begin_file();
-                        if (tid < (int)fd[(size_t)i].by_tid.size()) {
-                            std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
-                            window_records(v, w.cursor[(size_t)i], wb, we, w.sel);
-                            for (size_t j : w.sel) {
-                                w.pb.add(v[j], 0, false);
-                                if (remove_overlaps) w.pb.depth_clip.push_back(clips[(size_t)i][(size_t)tid][j]);
-                            }
+            const int rc = run_window_rounds(workers, wins, fp, "depth", [&](WinWorker &w, int64_t wb, int64_t we) {
+                w.pb.clear();
+                for (int i = 0; i < nfn; ++i) {
+                    w.pb.begin_file();
+                    if (tid < (int)fd[(size_t)i].by_tid.size()) {
+                        std::vector<Record> &v = fd[(size_t)i].by_tid[(size_t)tid];
+                        window_records(v, w.cursor[(size_t)i], wb, we, w.sel);
+                        for (size_t j : w.sel) {
+                            w.pb.add(v[j], 0, false);
+                            if (remove_overlaps) w.pb.depth_clip.push_back(clips[(size_t)i][(size_t)tid][j]);
                         }
                     }
-                    w.pb.finish();
-                    b200_batch_t batch = w.pb.view(tid, h.lens[(size_t)tid], h.names[(size_t)tid], nullptr);
-                    b200_stage_conf_t wsc = sc; wsc.beg = wb; wsc.end = we;
-                    b200_stage_stats_t st;
-                    if (b200_stage(w.eng.e, &batch, &wsc, &st) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); return; }
-                    const size_t bound = (size_t)b200_depth_text_bound(w.eng.e);
-                    if (w.out.size() < bound + 64) w.out.resize(bound + 64);
-                    if (b200_depth_text(w.eng.e, &dc, w.out.data(), w.out.size(), &w.need) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); }
-                });
-                for (auto &t : th) t.join();
-                for (size_t t = 0; t < m; ++t) {
-                    if (workers[t]->rc != 0) { fprintf(stderr, "samtools depth: %s\n", workers[t]->err.c_str()); return -1; }
-                    write_all(fp, workers[t]->out, workers[t]->need);
                 }
-            }
+                w.pb.finish();
+                b200_batch_t batch = w.pb.view(tid, h.lens[(size_t)tid], h.names[(size_t)tid], nullptr);
+                b200_stage_conf_t wsc = sc; wsc.beg = wb; wsc.end = we;
+                b200_stage_stats_t st;
+                if (b200_stage(w.eng.e, &batch, &wsc, &st) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); return; }
+                const size_t bound = (size_t)b200_depth_text_bound(w.eng.e);
+                if (w.out.size() < bound + 64) w.out.resize(bound + 64);
+                if (b200_depth_text(w.eng.e, &dc, w.out.data(), w.out.size(), &w.need) != 0) { w.rc = -1; w.err = b200_last_error(w.eng.e); }
+            });
+            if (rc != 0) return -1;
             return 1;
         }
         std::fill(cursor.begin(), cursor.end(), 0);

@@ -11,7 +11,7 @@ if [ -f "$stamp" ] && [ -f tests/emul/_build/b200samtools_emul ] && [ -f tests/e
    [ -z "$(find samtools_b200/csrc include tests/emul tests/compat oracle -maxdepth 2 -type f \( -name '*.cpp' -o -name '*.h' -o -name '*.hpp' -o -name '*.cuh' -o -name '*.c' -o -name '*.sh' -o -name Makefile \) -newer "$stamp" 2>/dev/null | head -1)" ]; then
     exit 0
 fi
-touch tests/emul/_build/.stamp.new
+touch tests/emul/_build/.stamp.new.$$
 g++ -std=c++17 -O1 -g -ffp-contract=off -Wall -Wno-unused-function -o tests/emul/_build/b200samtools_emul.tmp$$ \
     samtools_b200/csrc/host/cli.cpp samtools_b200/csrc/host/hts_io.cpp tests/emul/emul_engine.cpp -lz
 # the htslib-compatible iterator tier (plp_compat.cpp) + its test client, on the emulation harness
@@ -31,4 +31,4 @@ g++ -std=c++17 -O2 -ffp-contract=off -Wno-unknown-pragmas -o tests/emul/_build/b
     -Loracle/_build -loracle -Wl,-rpath,"$PWD/oracle/_build" -lz -lm
 
 for f in b200samtools_emul baq_host plbuf_dump_emul plp_dump_emul ref_bam_plbuf.o; do if [ -f tests/emul/_build/$f.tmp$$ ]; then mv -f tests/emul/_build/$f.tmp$$ tests/emul/_build/$f; fi; done
-mv -f tests/emul/_build/.stamp.new tests/emul/_build/.stamp
+mv -f tests/emul/_build/.stamp.new.$$ tests/emul/_build/.stamp
