@@ -2,10 +2,14 @@
 // Interface and semantics: include/b200_htslib_compat.h (htslib sam.h bam_plp_* / bam_mplp_*;
 // reference call sites bam_plbuf.c:40-66, bam_plcmd.c:581-607, coverage.c:572-589).
 //
-// One iterator = one engine handle.  The reads of one reference sequence are pulled (or
-// pushed), packed into the SoA batch image, staged once, and the device returns every
-// (read, column) entry -- the bam_pileup1_t fields -- column-major; next()/auto() then walk
-// that table.  With overlaps enabled the tweaked qualities are copied back into the
+// One iterator = one engine handle.  Reads are pulled (or pushed) until a WINDOW is complete -- the reference sequence
+// changes, the input ends, or the collected reads exceed a payload budget (B200_PLP_WINDOW_BYTES, default 256 MiB of
+// bases) -- then packed into the SoA batch image and staged, and the device returns every (read, column) entry -- the
+// bam_pileup1_t fields -- column-major; next()/auto() walk that table.  A window cut inside a reference sequence ends at
+// the start of the read that triggered it: every read that starts before it is in hand, so all columns below the cut can be
+// served; the reads reaching beyond the cut stay (the halo, exactly the -r rule of bam_plcmd.c:550-554) and are staged again
+// with the next window, which reports only columns from the cut on.  Host memory is bounded by the budget, and a push /
+// next client sees columns long before the reference sequence ends.  With overlaps enabled the tweaked qualities are copied back into the
 // iterator's read copies, which is what the caller sees through plp[i].b, as in htslib.
 #include "../../../include/b200_htslib_compat.h"
 #include "../../../include/b200_pileup.h"
@@ -41,6 +45,15 @@ namespace {
 constexpr int64_t kPosMax = ((int64_t)INT32_MAX << 32) | UINT32_MAX;
 constexpr int64_t kSlabCols = 1 << 20;
 
+// one past the last reference position of a record (pos + reference length of its CIGAR; zero-length: pos)
+int64_t read_end(const bam1_t *b)
+{
+    const uint32_t *cg = bam_get_cigar(b);
+    int64_t e = b->core.pos;
+    for (uint32_t k = 0; k < b->core.n_cigar; ++k) { const int op = cg[k] & 0xf; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) e += cg[k] >> 4; }
+    return e;
+}
+
 uint32_t name_bit(const char *s)
 {
     uint32_t h = (uint32_t)*s;
@@ -58,7 +71,12 @@ struct b200_plp {
     bam1_t *tmp = nullptr;                 // callback target
     std::vector<bam1_t *> accum;           // reads of the contig being collected
     std::vector<bam1_t *> batch;           // reads of the contig being served
-    bam1_t *pending = nullptr;             // first read of the next contig
+    bam1_t *pending = nullptr;             // the read that completed the window: first read of the next contig, or of the next window
+    bool cut = false;                      // pending continues the SAME reference sequence (window cut at its start)
+    int64_t serve_beg = -1, serve_end = kPosMax;   // columns [serve_beg, serve_end) of the staged batch are handed out
+    int64_t next_beg = -1;                 // where the next window of the current reference sequence starts (-1: at its first read)
+    size_t accum_bytes = 0, budget = (size_t)256 << 20;
+    std::vector<uint8_t> accum_done, batch_done;   // read's pair overlap was already tweaked in an earlier window (halo reads)
     std::vector<bam_pileup_cd> accum_cd, batch_cd; bam_pileup_cd pending_cd;   // client data of the same reads
     bam_plp_cd_f construct = nullptr, destruct = nullptr;
     int last_tid = -1; hts_pos_t last_pos = -1;
@@ -109,7 +127,7 @@ static int stage_batch(b200_plp *it)
         it->seq4.resize((qo + (uint64_t)c.l_qseq + 1) / 2 + 1, 0);
         for (int32_t k = 0; k < c.l_qseq; ++k) { const uint64_t m = qo + (uint64_t)k; it->seq4[m >> 1] |= (uint8_t)(bam_seqi(s, k) << ((~m & 1) << 2)); }
         uint8_t rb = 0; int64_t pv = -1;
-        if (it->overlaps) {
+        if (it->overlaps && !it->batch_done[i]) {   // a halo read whose pair was tweaked in an earlier window takes no part again
             const char *qn = bam_get_qname(b);
             auto f = names.find(qn);
             if (f != names.end()) { pv = f->second; f->second = (int64_t)i; } else names.emplace(qn, (int64_t)i);
@@ -128,7 +146,8 @@ static int stage_batch(b200_plp *it)
     bt.tid = it->tid; bt.tid_len = 0; bt.tid_name = "";
     b200_stage_conf_t sc; memset(&sc, 0, sizeof sc);
     sc.mode = B200_MODE_MPILEUP; sc.overlaps = it->overlaps; sc.max_depth = it->maxcnt;
-    sc.beg = it->batch[0]->core.pos; sc.end = kPosMax;   // filters are the callback's business (bam_plp_push drops only unmapped reads)
+    // filters are the callback's business (bam_plp_push drops only unmapped reads)
+    sc.beg = it->serve_beg >= 0 ? it->serve_beg : it->batch[0]->core.pos; sc.end = it->serve_end;
     b200_stage_stats_t st;
     if (b200_stage(it->eng, &bt, &sc, &st) != 0) { fprintf(stderr, "[b200 bam_plp] %s\n", b200_last_error(it->eng)); return -1; }
     it->win_base = sc.beg; it->n_cols = st.n_cols;
@@ -136,6 +155,8 @@ static int stage_batch(b200_plp *it)
         std::vector<uint8_t> q(it->qual.size() + 8);
         if (b200_fetch_qual(it->eng, q.data(), it->qual.size()) != 0) return -1;
         for (size_t i = 0; i < n; ++i) memcpy(bam_get_qual(it->batch[i]), q.data() + it->qual_off[i], (size_t)it->batch[i]->core.l_qseq);
+        // both mates staged together -> their tweak has happened (and is now in the copies): not again in a later window
+        for (size_t i = 0; i < n; ++i) if (it->prev[i] >= 0) { it->batch_done[i] = 1; it->batch_done[(size_t)it->prev[i]] = 1; }
     }
     it->col = 0; it->slab_beg = it->slab_end = 0; it->ent_pos = 0;
     return 0;
@@ -164,7 +185,23 @@ static int load_slab(b200_plp *it)
 static const bam_pileup1_t *serve(b200_plp *it, int *_tid, hts_pos_t *_pos, int *_n)
 {
     while (it->serving) {
-        if (it->col >= it->n_cols) { it->serving = false; free_reads(it, it->batch, it->batch_cd); break; }
+        if (it->col >= it->n_cols) {
+            it->serving = false;
+            if (it->serve_end < kPosMax) {
+                // window cut inside the reference sequence: reads reaching beyond the cut go back to the front of the collection
+                std::vector<bam1_t *> keep; std::vector<bam_pileup_cd> keep_cd; std::vector<uint8_t> keep_done; size_t bytes = 0;
+                for (size_t i = 0; i < it->batch.size(); ++i) {
+                    bam1_t *b = it->batch[i];
+                    if (read_end(b) > it->serve_end) { keep.push_back(b); keep_cd.push_back(it->batch_cd[i]); keep_done.push_back(it->batch_done[i]); bytes += (size_t)b->core.l_qseq; }
+                    else { if (it->destruct) it->destruct(it->data, b, &it->batch_cd[i]); bam_destroy1(b); }
+                }
+                it->batch.clear(); it->batch_cd.clear(); it->batch_done.clear();
+                keep.insert(keep.end(), it->accum.begin(), it->accum.end()); keep_cd.insert(keep_cd.end(), it->accum_cd.begin(), it->accum_cd.end());
+                keep_done.insert(keep_done.end(), it->accum_done.begin(), it->accum_done.end());
+                it->accum.swap(keep); it->accum_cd.swap(keep_cd); it->accum_done.swap(keep_done); it->accum_bytes += bytes;
+            } else { free_reads(it, it->batch, it->batch_cd); it->batch_done.clear(); }
+            break;
+        }
         if (it->col >= it->slab_end) { if (load_slab(it) != 0) { it->error = true; *_n = -1; return nullptr; } }
         while (it->col < it->slab_end) {
             const uint32_t n = it->col_n[(size_t)(it->col - it->slab_beg)];
@@ -189,10 +226,14 @@ static const bam_pileup1_t *serve(b200_plp *it, int *_tid, hts_pos_t *_pos, int 
 // the collected contig becomes the served one
 static int start_serving(b200_plp *it)
 {
-    it->batch.swap(it->accum); it->batch_cd.swap(it->accum_cd);
-    it->accum.clear(); it->accum_cd.clear();
+    it->batch.swap(it->accum); it->batch_cd.swap(it->accum_cd); it->batch_done.swap(it->accum_done);
+    it->accum.clear(); it->accum_cd.clear(); it->accum_done.clear(); it->accum_bytes = 0;
     if (it->batch.empty()) return 0;
     it->tid = it->batch[0]->core.tid;
+    // the previous window of this reference sequence ended at next_beg; this one ends at the start of the read that cut it
+    it->serve_beg = it->next_beg;
+    it->serve_end = it->cut ? it->pending->core.pos : kPosMax;
+    it->next_beg = it->cut ? it->serve_end : -1;
     if (stage_batch(it) != 0) { it->error = true; return -1; }
     it->serving = true;
     return 0;
@@ -208,6 +249,7 @@ bam_plp_t bam_plp_init(bam_plp_auto_f func, void *data)
     if (const char *s = getenv("B200_DEVICE")) dev = atoi(s);
     if (b200_engine_create(dev, &it->eng) != 0) { delete it; return nullptr; }
     it->tmp = bam_init1();
+    if (const char *s = getenv("B200_PLP_WINDOW_BYTES")) { const long long v = atoll(s); if (v > 0) it->budget = (size_t)v; }
     return it;
 }
 
@@ -225,6 +267,8 @@ void bam_plp_reset(bam_plp_t it)
     free_reads(it, it->accum, it->accum_cd); free_reads(it, it->batch, it->batch_cd);
     free_pending(it);
     it->serving = false; it->eof = false; it->error = false; it->last_tid = -1; it->last_pos = -1;
+    it->cut = false; it->serve_beg = -1; it->serve_end = kPosMax; it->next_beg = -1; it->accum_bytes = 0;
+    it->accum_done.clear(); it->batch_done.clear();
 }
 
 void bam_plp_set_maxcnt(bam_plp_t it, int maxcnt) { it->maxcnt = maxcnt; }
@@ -245,14 +289,19 @@ int bam_plp_push(bam_plp_t it, const bam1_t *b)
     bam1_t *c = bam_init1();
     if (!c || !bam_copy1(c, b)) { it->error = true; return -1; }
     bam_pileup_cd cd; cd.i = 0;
-    if (!it->accum.empty() && it->accum[0]->core.tid != c->core.tid) {
-        // a new contig begins: it waits until the current one has been handed out
+    const bool new_tid = !it->accum.empty() && it->accum[0]->core.tid != c->core.tid;
+    // a window is cut at this read when the budget is spent and the read opens a new position (all reads starting before it
+    // are in hand) beyond the start of the window under collection
+    const bool over = !new_tid && !it->accum.empty() && it->accum_bytes >= it->budget && c->core.pos > it->accum.back()->core.pos &&
+                      c->core.pos > (it->next_beg >= 0 ? it->next_beg : it->accum[0]->core.pos);
+    if (new_tid || over) {
+        // it waits until the window under collection has been handed out
         if (it->pending) { it->error = true; bam_destroy1(c); return -1; }
         if (it->construct) it->construct(it->data, c, &cd);
-        it->pending = c; it->pending_cd = cd;
+        it->pending = c; it->pending_cd = cd; it->cut = over;
     } else {
         if (it->construct) it->construct(it->data, c, &cd);
-        it->accum.push_back(c); it->accum_cd.push_back(cd);
+        it->accum.push_back(c); it->accum_cd.push_back(cd); it->accum_done.push_back(0); it->accum_bytes += (size_t)c->core.l_qseq;
     }
     return 0;
 }
@@ -267,7 +316,10 @@ const bam_pileup1_t *bam_plp64_next(bam_plp_t it, int *_tid, hts_pos_t *_pos, in
         // a contig is complete when a read of another contig has arrived, or at end of input
         if (it->pending || (it->eof && !it->accum.empty())) {
             if (start_serving(it) != 0) { *_n = -1; return nullptr; }
-            if (it->pending) { it->accum.push_back(it->pending); it->accum_cd.push_back(it->pending_cd); it->pending = nullptr; }
+            if (it->pending) {
+                it->accum.push_back(it->pending); it->accum_cd.push_back(it->pending_cd); it->accum_done.push_back(0);
+                it->accum_bytes += (size_t)it->pending->core.l_qseq; it->pending = nullptr; it->cut = false;
+            }
             continue;
         }
         return nullptr;

@@ -12,7 +12,8 @@
 // and every constructed read must be destructed exactly once
 static long n_ctor = 0, n_dtor = 0, cd_bad = 0;
 static int ctor(void *, const bam1_t *, bam_pileup_cd *cd) { cd->i = ++n_ctor; return 0; }
-static int dtor(void *, const bam1_t *, bam_pileup_cd *cd) { if (cd->i < 1 || cd->i > n_ctor) ++cd_bad; cd->i = -1; ++n_dtor; return 0; }
+static std::map<const bam1_t *, int64_t> seen;     // client data last seen with a live read (the iterator may recycle a freed read's address)
+static int dtor(void *, const bam1_t *b, bam_pileup_cd *cd) { if (cd->i < 1 || cd->i > n_ctor) ++cd_bad; cd->i = -1; ++n_dtor; seen.erase(b); return 0; }
 
 int main(int argc, char **argv)
 {
@@ -30,7 +31,6 @@ int main(int argc, char **argv)
     if (!it) { fprintf(stderr, "plp_dump: no CUDA pileup engine\n"); return 1; }
     if (overlaps) bam_mplp_init_overlaps(it);
     if (hooks) { bam_mplp_constructor(it, ctor); bam_mplp_destructor(it, dtor); }
-    std::map<const bam1_t *, int64_t> seen;
     kstring_t ks = {0, 0, nullptr};
     bam_mplp_set_maxcnt(it, maxcnt);
     std::vector<int> n_plp((size_t)n); std::vector<const bam_pileup1_t *> plp((size_t)n);

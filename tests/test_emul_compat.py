@@ -47,3 +47,19 @@ def test_reference_bam_plbuf_rides_on_the_tier(f, dump_emul, oracle_bin, corpus)
     want = subprocess.run([oracle_bin, 'pileup-dump', os.path.join(corpus, f)], capture_output=True)
     assert got.returncode == 0, got.stderr[-300:]
     assert got.stdout == want.stdout and len(got.stdout) > 100
+
+
+@pytest.mark.parametrize('budget', ['1', '400', '5000'])
+@pytest.mark.parametrize('args,files', golden_cases.COMPAT_CASES, ids=golden_cases.COMPAT_IDS)
+def test_iterator_tier_windows(args, files, budget, dump_emul, oracle_bin, corpus, monkeypatch):
+    """B200_PLP_WINDOW_BYTES: the tier cuts a reference sequence into windows once the collected reads exceed a payload budget
+    (cut at the start of the read that exceeded it, halo reads staged again, columns served window by window).  With budgets of
+    1 / 400 / 5000 bases every case is cut many times -- mate overlaps across a cut, deletions, the max-depth case, the k-way
+    merge of three files, the hooks -- and must dump exactly what htslib's iterator yields."""
+    monkeypatch.setenv('B200_PLP_WINDOW_BYTES', budget)
+    paths = [os.path.join(corpus, f) for f in files]
+    got = subprocess.run([dump_emul, '-c', *args, *paths], capture_output=True)
+    want = subprocess.run([oracle_bin, 'pileup-dump', *args, *paths], capture_output=True)
+    assert got.returncode == 0, got.stderr[-300:]
+    assert got.stdout == want.stdout
+    assert b'bad=0' in got.stderr
