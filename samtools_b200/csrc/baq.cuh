@@ -492,8 +492,8 @@ int launch_baq(b200_engine *e, const RawSoA &r, const b200_stage_conf_t &cf)
         const int blocks = (int)((warps + BAQR_THREADS / 32 - 1) / (BAQR_THREADS / 32));
         warps = (int64_t)blocks * (BAQR_THREADS / 32);
         if (ensure(e, e->baq_f, e->cap_baq_f, (size_t)warps * slab_units * 2)) return -1;
-        static bool attr_set = false;
-        if (!attr_set) { CK(cudaFuncSetAttribute(k_baq_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, BAQR_STAGE_BYTES)); attr_set = true; }
+        // per device (function attributes are), so once per engine handle -- not once per process: a second GPU's handle needs it too
+        if (!e->baq_attr_set) { CK(cudaFuncSetAttribute(k_baq_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, BAQR_STAGE_BYTES)); e->baq_attr_set = true; }
         k_baq_reg<<<blocks, BAQR_THREADS, BAQR_STAGE_BYTES, e->stream>>>(r, plan, idx2, n_idx2, (double2 *)e->baq_f, slab_units, lqmax, e->ref_codes, e->d_q2p, e->d_qthr, cf.baq != 3); e->launches++;
         CK(cudaGetLastError());
     }

@@ -22,6 +22,7 @@ struct b200_engine {
     size_t qual_bytes = 0, n_cigar_total = 0;
     uint32_t smem_text = 24 * 1024;
     void *d_gfmt = nullptr;      // device copy of the gather's parameter block (cold paths)
+    bool baq_attr_set = false;   // k_baq_reg's dynamic shared-memory attribute has been raised on this handle's device
     int use_tma = 1, general = 0;
 
     // raw SoA image of the staged records
