@@ -11,18 +11,16 @@
 //               [lo,hi) read ranges, entry strings (2 B per read base), look-back status words, output text
 //
 // Column stage for text (mpileup, depth): sizes -> offsets -> bytes, no inter-CTA waiting.
-//   (1) a size pass gives every column its line length (mpileup: order-free streaming pass
-//       over the reads, mpileup_ss.cuh; depth: thread per column);
+//   (1) sizes.  mpileup, one input file (the default path, mpileup_ent.cuh / mpileup_ss.cuh): a READ-major entry pass formats
+//       every read into 16-bit entries (eight bases per lane, SIMD within a register) and feeds order-free line-length sums
+//       (coverage difference array, failing bases, extra bytes); a scan + a per-column kernel turn them into line lengths.
+//       General mpileup path (several files, -O, host string columns) and depth: thread per column.
 //   (2) a single-pass scan of 128-column tile totals gives every tile its byte offset;
-//   (3) the write pass: one thread per reference position walks the reads whose slice covers
-//       its 32-column group (descriptors and quality/base bytes software-pipelined), formats
-//       its line into shared memory laid out with the destination's 16-byte phase, and the
-//       tile leaves the SM as one cp.async.bulk (TMA) shared->global store plus <16 B edges.
-// HBM traffic per column is ~ the algorithmic bytes: reads are fetched once per pass through
-// L1/L2 (neighbouring columns share them), text is written once, fully coalesced.
-// Selectable variants kept for A/B and as mutual cross-checks (tests require identical bytes):
-// read-major sizing / write (mpileup_rm.cuh), 4 columns per thread (mpileup_w4.cuh), and the
-// first design, a single chained launch with decoupled look-back (k_mpileup).
+//   (3) bytes.  Default mpileup: the gather -- a warp per 32-column group fetches the entry strings with wide loads (lanes along
+//       the reads), parks them in shared-memory rows and appends them to the lines (lanes along the columns).  Other paths:
+//       one thread per reference position formats its line.  Either way a tile's text is laid out in shared memory with the
+//       destination's 16-byte phase and leaves the SM through cp.async.bulk (TMA) shared->global stores plus <16 B edges.
+// HBM traffic per column is ~ the algorithmic bytes (+ the entry strings, written and read once).
 // No tensor cores: integer/byte work.
 #include <cuda_runtime.h>
 #include <stdint.h>
